@@ -1,0 +1,249 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference simulator.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Every fixture is a small .npz holding (a) the oracle config struct bytes extracted from the
+reference's own asset objects (so the fixtures are self-contained on the GPU box, where
+/root/reference does not exist), (b) the inputs (actions) and (c) the reference outputs.  Map
+geometry results come from the Shapely stand-in of oracle/ref_harness.py (Shapely is not installed).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle as O  # noqa: E402
+from oracle import ref_harness as H  # noqa: E402
+
+
+def struct_bytes(s) -> np.ndarray:
+    return np.frombuffer(ctypes.string_at(ctypes.byref(s), ctypes.sizeof(s)), dtype=np.uint8).copy()
+
+
+def events_bits(s: str) -> int:
+    bits = 0
+    rest = s
+    for i, ev in enumerate(O.EVENT_STRINGS):
+        if ev in rest:
+            bits |= 1 << i
+            rest = rest.replace(ev, '')
+    assert rest == '', f"unparsed events: {rest!r}"
+    return bits
+
+
+def ship_vec(asset):
+    sm = asset.ship_model
+    omega = sm.ship_machinery_model.omega if hasattr(sm, "ship_machinery_model") else 0.0
+    return [float(sm.north), float(sm.east), float(sm.yaw_angle), float(sm.forward_speed),
+            float(sm.sideways_speed), float(sm.yaw_rate), float(omega), float(asset.auto_pilot.navigate.e_ct)]
+
+
+def ctrl_vec(asset):
+    ap = asset.auto_pilot
+    pid = ap.heading_controller.ship_heading_controller
+    if hasattr(asset, "speed_controller"):
+        sc = asset.speed_controller.ship_speed_controller
+        sp = [float(sc.error_i), float(sc.prev_error), 0.0]
+    else:
+        tc = asset.throttle_controller
+        sp = [float(tc.ship_speed_controller.error_i), 0.0, float(tc.shaft_speed_controller.error_i)]
+    return [float(ap.navigate.e_ct_int), float(pid.error_i), float(pid.prev_error)] + sp + [float(asset.ship_model.int.time)]
+
+
+# ------------------------------------------------------------------------------------------------
+def bare_rollout(kind: str, dt, who: int, n_steps: int, mode="PTI", post_reset=False):
+    """Bare ship + controllers loop (KAT1 / KAT3 of SURVEY.md section 8c)."""
+    args = H.Args(time_step=dt)
+    if kind == "simple":
+        assets, _ = H.build_colav_assets(args, obs_route="obs_ship_route_nonIW.txt")
+    else:
+        assets, _ = H.build_rl_assets(args, mode=mode)
+    a = assets[who]
+    sm = a.ship_model
+    if post_reset:
+        sm.reset()
+        (a.throttle_controller if kind == "detailed" else a.speed_controller).reset()
+        a.auto_pilot.reset()
+    cfg = O.ship_config_from_asset(a, post_reset=post_reset and kind == "detailed")
+    states = np.zeros((n_steps, 8))
+    ctrl = np.zeros((n_steps, 7))
+    wpt = np.zeros(n_steps, dtype=np.int32)
+    for i in range(n_steps):
+        rud = a.auto_pilot.rudder_angle_from_sampled_route(sm.north, sm.east, sm.yaw_angle)
+        if kind == "simple":
+            cmd = a.speed_controller.thrust(a.desired_forward_speed, sm.forward_speed)
+            sm.update_differentials(thrust_force=cmd, rudder_angle=rud)
+        else:
+            cmd = a.throttle_controller.throttle(speed_set_point=a.desired_forward_speed,
+                                                 measured_speed=sm.forward_speed,
+                                                 measured_shaft_speed=sm.forward_speed)
+            sm.update_differentials(engine_throttle=cmd, rudder_angle=rud)
+        sm.integrate_differentials()
+        sm.int.next_time()
+        states[i] = ship_vec(a)
+        ctrl[i] = ctrl_vec(a)
+        wpt[i] = a.auto_pilot.next_wpt
+    # keep the first 256 steps, then every 16th, and always the last
+    keep = np.unique(np.concatenate([np.arange(min(256, n_steps)), np.arange(15, n_steps, 16), [n_steps - 1]]))
+    return dict(cfg=struct_bytes(cfg), n_steps=n_steps, step_index=keep + 1, states=states[keep],
+                ctrl=ctrl[keep], next_wpt=wpt, dt_shaft=cfg.dt_shaft)
+
+
+def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None, obs_init=None, sim_time=10000):
+    """Episode of run_colav.MultiShipEnv ("colav") or rl_env MultiShipRLEnv ("rl"): KAT2 / KAT4."""
+    args = H.Args(time_step=dt, collav_mode=collav)
+    if kind == "colav":
+        env, assets = H.make_colav_iw_env(args, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
+        env_kind = O.ENV_COLAV_IW
+    else:
+        env, assets = H.make_rl_env(args, mode=mode, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
+        env_kind = O.ENV_RL
+    cfg = O.env_config_from_assets(assets, env.map, args, env_kind)
+    obs0 = env.reset()
+    n = len(actions)
+    out = dict(cfg=struct_bytes(cfg), actions=np.asarray(actions, dtype=np.float64), obs0=np.asarray(obs0),
+               obs=np.zeros((n, 8), np.float32), reward=np.zeros(n), done=np.zeros(n, np.int32),
+               events=np.zeros(n, np.int32), terminal=np.zeros(n, np.int32), test_stop=np.zeros(n, np.int32),
+               obs_stop=np.zeros(n, np.int32), n_log=np.zeros(n, np.int32), k_test=np.zeros(n, np.int32),
+               k_obs=np.zeros(n, np.int32), test_state=np.zeros((n, 8)), obs_state=np.zeros((n, 8)),
+               test_ctrl=np.zeros((n, 7)), obs_ctrl=np.zeros((n, 7)), travel_dist=np.zeros(n),
+               n_valid=0)
+    for j, a in enumerate(actions):
+        res = env.step(np.array([a], dtype=np.float64))
+        if kind == "colav":
+            o, d, info = res
+            r = 0.0
+        else:
+            o, r, d, info = res
+        out["obs"][j] = o
+        out["reward"][j] = r
+        out["done"][j] = bool(d)
+        out["events"][j] = events_bits(info['events'])
+        out["terminal"][j] = bool(info['terminal'])
+        out["test_stop"][j] = bool(info['test_ship_stop'])
+        out["obs_stop"][j] = bool(info['obs_ship_stop'])
+        out["n_log"][j] = len(assets[1].ship_model.simulation_results['time [s]'])
+        out["k_test"][j] = assets[0].auto_pilot.next_wpt
+        out["k_obs"][j] = assets[1].auto_pilot.next_wpt
+        out["test_state"][j] = ship_vec(assets[0])
+        out["obs_state"][j] = ship_vec(assets[1])
+        out["test_ctrl"][j] = ctrl_vec(assets[0])
+        out["obs_ctrl"][j] = ctrl_vec(assets[1])
+        out["travel_dist"][j] = env.travel_dist
+        out["n_valid"] = j + 1
+        if d:
+            break
+    out["obs_route_north"] = np.asarray(assets[1].auto_pilot.navigate.north, dtype=np.float64)
+    out["obs_route_east"] = np.asarray(assets[1].auto_pilot.navigate.east, dtype=np.float64)
+    if kind == "rl":
+        out["substep_rewards"] = np.asarray(env.reward_tracker.total, dtype=np.float64)
+    # per-substep trajectory of both ships from the reference's own log (pre-integration rows)
+    for who, name in ((0, "test"), (1, "obs")):
+        sr = assets[who].ship_model.simulation_results
+        out[f"{name}_log_north"] = np.asarray(sr['north position [m]'], dtype=np.float64)
+        out[f"{name}_log_east"] = np.asarray(sr['east position [m]'], dtype=np.float64)
+        out[f"{name}_log_ect"] = np.asarray(sr['cross track error [m]'], dtype=np.float64)
+    return out
+
+
+def noniw_run(dt, collav="none", max_steps=4000, test_init=None, obs_init=None, use_reset=False):
+    """run_colav.MultiShipNonIWEnv: init_step() then _step() until combined_done (config 1)."""
+    args = H.Args(time_step=dt, collav_mode=collav)
+    env, assets = H.make_colav_noniw_env(args, test_init=test_init, obs_init=obs_init)
+    cfg = O.env_config_from_assets(assets, env.map, args, O.ENV_COLAV_NONIW)
+    if use_reset:
+        env.reset()
+    else:
+        env.init_step()
+    obs, ev, term, ts, os_, done, tst, ost, kt, ko = [], [], [], [], [], [], [], [], [], []
+    for _ in range(max_steps):
+        o, d, info = env._step()
+        obs.append(o); ev.append(events_bits(info['events'])); term.append(bool(info['terminal']))
+        ts.append(bool(info['test_ship_stop'])); os_.append(bool(info['obs_ship_stop'])); done.append(bool(d))
+        tst.append(ship_vec(assets[0]) + [assets[0].ship_model.int.time])
+        ost.append(ship_vec(assets[1]) + [assets[1].ship_model.int.time])
+        kt.append(assets[0].auto_pilot.next_wpt); ko.append(assets[1].auto_pilot.next_wpt)
+        if d:
+            break
+    return dict(cfg=struct_bytes(cfg), obs=np.asarray(obs, np.float32), events=np.asarray(ev, np.int32),
+                terminal=np.asarray(term, np.int32), test_stop=np.asarray(ts, np.int32),
+                obs_stop=np.asarray(os_, np.int32), done=np.asarray(done, np.int32),
+                test_state=np.asarray(tst), obs_state=np.asarray(ost), k_test=np.asarray(kt, np.int32),
+                k_obs=np.asarray(ko, np.int32), use_reset=int(use_reset))
+
+
+def save(name, d):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **d)
+    print(f"{name:40s} {os.path.getsize(path) / 1024:8.1f} KiB")
+
+
+def main():
+    assert H.reference_available(), "needs /root/reference"
+    deg = np.deg2rad
+    kat_actions = deg(np.array([-2, 0, 5, -5, 10, 0, 0, 0, 0], dtype=np.float64))
+    rng = np.random.default_rng(20261018)
+
+    # --- bare ship loops (KAT1, KAT3) ---
+    for dt in (1, 4, 30):
+        for who in (0, 1):
+            save(f"bare_simple_dt{dt}_{'test' if who == 0 else 'obs'}", bare_rollout("simple", dt, who, 10000))
+    for mode in ("PTI", "PTO", "MEC"):
+        save(f"bare_detailed_{mode}_dt4_prereset", bare_rollout("detailed", 4, 0, 4000, mode=mode))
+        save(f"bare_detailed_{mode}_dt4_postreset", bare_rollout("detailed", 4, 0, 4000, mode=mode, post_reset=True))
+    save("bare_detailed_PTI_dt4_obs_postreset", bare_rollout("detailed", 4, 1, 4000, post_reset=True))
+
+    # --- IW episodes (KAT2, KAT4) ---
+    save("colav_iw_dt4_kat", iw_episode("colav", 4, kat_actions))
+    save("rl_dt4_kat", iw_episode("rl", 4, kat_actions))
+    for i in range(4):
+        acts = rng.uniform(-np.pi / 6, np.pi / 6, size=9)
+        save(f"colav_iw_dt4_rand{i}", iw_episode("colav", 4, acts))
+        save(f"rl_dt4_rand{i}", iw_episode("rl", 4, acts))
+    # large scoping angles: waypoints land on islands / outside the map -> sampling failure path
+    save("colav_iw_dt4_fail", iw_episode("colav", 4, deg(np.array([10., 30., 30., 30., 30., 30., 30., 30., 30.]))))
+    save("rl_dt4_fail", iw_episode("rl", 4, deg(np.array([10., -30., -30., -30., -30., -30., -30., -30., -30.]))))
+    # small scoping angles keep the obstacle ship on the test ship's track -> "Ships collision!"
+    # (action rows found by scanning 20000 random episodes with the oracle)
+    save("rl_dt4_collision", iw_episode("rl", 4, np.array(
+        [-0.04947389, 0.02654783, 0.00399436, -0.01783045, 0.03020418, -0.02060939, -0.00486969, -0.03832306,
+         -0.01014598])))
+    save("colav_iw_dt4_collision", iw_episode("colav", 4, np.array(
+        [0.02003677, -0.03365987, -0.01086403, -0.05174993, -0.0248715, -0.00825309, -0.04126783, 0.01394448,
+         -0.01252194])))
+    # obstacle ship navigational failure (cross-track error > 500 m)
+    nav = np.array([-0.07864699, -0.28520827, 0.10994892, -0.21765305, -0.17804338, 0.00772443, -0.18959464,
+                    -0.25623406, -0.51439543])
+    save("rl_dt4_obsnavfail", iw_episode("rl", 4, nav))
+    save("colav_iw_dt4_obsnavfail", iw_episode("colav", 4, nav))
+    # test ship starts next to island 1 and runs aground within a few steps
+    aground = dict(test_init=dict(initial_north_position_m=2380.0, initial_east_position_m=200.0))
+    save("rl_dt4_testgrounding", iw_episode("rl", 4, kat_actions, **aground))
+    save("colav_iw_dt4_testgrounding", iw_episode("colav", 4, kat_actions, **aground))
+    # simulation time limit (sim_time = 1000 s -> 250 steps)
+    save("rl_dt4_timelimit", iw_episode("rl", 4, kat_actions, sim_time=1000))
+    save("colav_iw_dt4_timelimit", iw_episode("colav", 4, kat_actions, sim_time=1000))
+    save("rl_dt4_simple_collav", iw_episode("rl", 4, kat_actions, collav="simple"))
+    save("colav_iw_dt4_simple_collav", iw_episode("colav", 4, kat_actions, collav="simple"))
+    save("rl_dt10_kat", iw_episode("rl", 10, kat_actions))
+    save("rl_dt4_PTO", iw_episode("rl", 4, kat_actions, mode="PTO"))
+    save("rl_dt4_MEC", iw_episode("rl", 4, kat_actions, mode="MEC"))
+
+    # --- NonIW env (config 1) ---
+    save("colav_noniw_dt4", noniw_run(4))
+    save("colav_noniw_dt30", noniw_run(30))
+    save("colav_noniw_dt4_simple_collav", noniw_run(4, collav="simple"))
+    save("colav_noniw_dt4_reset", noniw_run(4, use_reset=True))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests: golden fixture loading and error metrics."""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# relative error is |a-b| / max(|b|, scale) with per-state scales
+# columns: N, E, psi, u, v, r, omega, e_ct
+STATE_SCALE = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1e-3, 1.0, 1.0])
+# columns of ctrl_vec: e_ct_int, hdg_err_i, hdg_prev_err, spd_err_i, spd_prev_err, shaft_err_i, time
+CTRL_SCALE = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
+REL_TOL = 1e-9          # BASELINE.json north_star tolerance (per state, over 10k steps)
+
+
+def golden(name: str):
+    return np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+
+
+def golden_names(prefix: str):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
+
+
+def struct_from_bytes(cls, arr):
+    s = cls()
+    raw = np.ascontiguousarray(arr, dtype=np.uint8).tobytes()
+    assert len(raw) == ctypes.sizeof(cls), (len(raw), ctypes.sizeof(cls))
+    ctypes.memmove(ctypes.byref(s), raw, len(raw))
+    return s
+
+
+def rel_err(a, b, scale):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), scale)
+
+
+def oracle_ship_vec(s) -> np.ndarray:
+    return np.array([s.north, s.east, s.yaw, s.u, s.v, s.r, s.omega, s.e_ct])
+
+
+def oracle_ctrl_vec(s, detailed: bool) -> np.ndarray:
+    if detailed:
+        sp = [s.spd_err_i, 0.0, s.shaft_err_i]
+    else:
+        sp = [s.spd_err_i, s.spd_prev_err, 0.0]
+    return np.array([s.e_ct_int, s.hdg_err_i, s.hdg_prev_err] + sp + [s.time])

@@ -1,0 +1,125 @@
+"""CPU tests: pin the C oracle (oracle/shipsim_oracle.c) against golden vectors produced by the
+unmodified Python reference (tests/golden/make_golden.py).  Flags, event bits, waypoint indices and
+step counts must match bit-exactly; FP64 states within REL_TOL = 1e-9 (dt <= 10; the dt = 30 case
+is the documented explicit-Euler amplification case, SURVEY.md section 7, bounded at 1e-7)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from helpers import (CTRL_SCALE, REL_TOL, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
+                     rel_err, struct_from_bytes)
+
+
+@pytest.mark.parametrize("name", golden_names("bare_"))
+def test_bare_ship_rollout(name):
+    g = golden(name)
+    cfg = struct_from_bytes(O.ShipConfig, g["cfg"])
+    n = int(g["n_steps"])
+    out, wpt, st = O.ship_rollout(cfg, n)
+    idx = g["step_index"] - 1
+    err = rel_err(out[idx], g["states"], STATE_SCALE)
+    tol = 1e-7 if "dt30" in name else REL_TOL
+    detailed = cfg.model_kind == O.MODEL_DETAILED
+    if detailed:
+        # The detailed model is only pinned while the ship is on its route (the env terminates at
+        # the route end, ~1300 steps at dt = 4).  Sailing on past the last waypoint puts the
+        # throttle/torque saturations into a limit cycle that amplifies 1-ulp differences
+        # (1e-14 at step 1500 -> 1e-6 at step 2900), so later rows are only sanity-bounded.
+        end_n, end_e = cfg.wp_north[cfg.n_wp - 1], cfg.wp_east[cfg.n_wp - 1]
+        d_end = np.hypot(g["states"][:, 0] - end_n, g["states"][:, 1] - end_e)
+        arrived = np.nonzero(d_end < 300.0)[0]
+        on_route = np.arange(len(d_end)) <= (arrived[0] if len(arrived) else len(d_end))
+        assert on_route.sum() > 280
+        assert err[on_route].max() < tol, (name, err[on_route].max(axis=0))
+        assert err.max() < 0.1
+    else:
+        assert err.max() < tol, (name, err.max(axis=0))
+        final_ctrl = oracle_ctrl_vec(st, detailed=False)
+        assert rel_err(final_ctrl, g["ctrl"][-1], CTRL_SCALE).max() < (1e-6 if "dt30" in name else REL_TOL)
+    # waypoint indices are bit-exact at every step
+    assert np.array_equal(wpt, g["next_wpt"])
+
+
+def _run_iw(name):
+    g = golden(name)
+    cfg = struct_from_bytes(O.EnvConfig, g["cfg"])
+    env = O.OracleEnv(cfg)
+    obs0 = env.reset()
+    assert np.array_equal(obs0, g["obs0"])
+    n = int(g["n_valid"])
+    detailed = cfg.ship[0].model_kind == O.MODEL_DETAILED
+    n_sub = 0
+    for j in range(n):
+        r = env.step(float(g["actions"][j]))
+        assert r.error == 0
+        n_sub += r.n_substeps
+        # integers / flags: bit exact
+        assert r.done == g["done"][j], (name, j)
+        assert r.events == g["events"][j], (name, j, O.events_to_string(r.events))
+        assert r.terminal == g["terminal"][j]
+        assert r.test_ship_stop == g["test_stop"][j]
+        assert r.obs_ship_stop == g["obs_stop"][j]
+        assert env.st.ship[0].next_wpt == g["k_test"][j]
+        assert env.st.ship[1].next_wpt == g["k_obs"][j]
+        assert env.st.ship[1].n_log == g["n_log"][j], (name, j, env.st.ship[1].n_log, g["n_log"][j])
+        # FP64 states
+        for who, key in ((0, "test"), (1, "obs")):
+            e = rel_err(oracle_ship_vec(env.st.ship[who]), g[key + "_state"][j], STATE_SCALE)
+            assert e.max() < REL_TOL, (name, j, key, e)
+            e = rel_err(oracle_ctrl_vec(env.st.ship[who], detailed), g[key + "_ctrl"][j], CTRL_SCALE)
+            assert e.max() < REL_TOL, (name, j, key, "ctrl", e)
+        assert rel_err(env.st.travel_dist, g["travel_dist"][j], 1.0) < REL_TOL
+        # float32 observation: allow 1 ulp of float32 where the FP64 value sits on a rounding boundary
+        np.testing.assert_allclose(np.array(r.obs[:]), g["obs"][j], rtol=2e-7, atol=1e-6)
+        if cfg.env_kind == O.ENV_RL:
+            assert rel_err(r.reward, g["reward"][j], 1e-3) < 1e-8, (name, j, r.reward, g["reward"][j])
+    route_n = np.array(env.st.ship[1].wp_north[: env.st.ship[1].n_wp])
+    route_e = np.array(env.st.ship[1].wp_east[: env.st.ship[1].n_wp])
+    assert rel_err(route_n, g["obs_route_north"], 1.0).max() < 1e-12
+    assert rel_err(route_e, g["obs_route_east"], 1.0).max() < 1e-12
+    return n_sub
+
+
+@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_"))
+def test_iw_episode(name):
+    _run_iw(name)
+
+
+@pytest.mark.parametrize("name", golden_names("colav_noniw_"))
+def test_noniw_run(name):
+    g = golden(name)
+    cfg = struct_from_bytes(O.EnvConfig, g["cfg"])
+    env = O.OracleEnv(cfg)
+    if int(g["use_reset"]):
+        env.reset()
+    else:
+        env.init_step()
+    n = len(g["done"])
+    tol = 1e-6 if "dt30" in name else REL_TOL
+    for i in range(n):
+        r = env._step()
+        assert r.done == g["done"][i], (name, i)
+        assert r.events == g["events"][i], (name, i)
+        assert r.terminal == g["terminal"][i] and r.test_ship_stop == g["test_stop"][i]
+        assert r.obs_ship_stop == g["obs_stop"][i]
+        assert env.st.ship[0].next_wpt == g["k_test"][i] and env.st.ship[1].next_wpt == g["k_obs"][i]
+        for who, key in ((0, "test_state"), (1, "obs_state")):
+            v = np.append(oracle_ship_vec(env.st.ship[who]), env.st.ship[who].time)
+            e = rel_err(v, g[key][i], np.append(STATE_SCALE, 1.0))
+            assert e.max() < tol, (name, i, key, e)
+        np.testing.assert_allclose(np.array(r.obs[:6]), g["obs"][i], rtol=2e-7, atol=1e-6)
+
+
+def test_struct_sizes_and_kat_numbers():
+    """KAT1 numbers quoted in SURVEY.md section 8c (bare SimpleShipModel, dt = 4)."""
+    g = golden("bare_simple_dt4_test")
+    cfg = struct_from_bytes(O.ShipConfig, g["cfg"])
+    out, wpt, _ = O.ship_rollout(cfg, 1000)
+    np.testing.assert_allclose(out[0, :6], [108.5, 114.72243186433546, 1.0471975511965976, 4.096500182368609,
+                                            0.13826982694737566, 0.00137588043814453], rtol=1e-13)
+    np.testing.assert_allclose(out[999, :6], [6479.760478596196, 13742.004396294615, 1.1872381223284336,
+                                              4.362949147831841, 0.7831900869036864, -0.0015340263572957782],
+                               rtol=1e-10)
+    assert wpt[0] == 1 and wpt[99] == 1 and wpt[999] == 4
