@@ -1,0 +1,458 @@
+// shipenv.cu -- host side of the C ABI declared in include/shipenv.h (handle, validation, launches).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared ...
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "shipenv.h"
+#include "shipenv_kernels.cuh"
+
+using senv::DevView;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess) return fail(SHIPENV_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int kBlock = 128;
+
+}  // namespace
+
+struct shipenv {
+  int device = 0;
+  long long num_envs = 0;
+  ShipEnvParams params;
+  ShipEnvParams* params_dev = nullptr;
+  ShipEnvBuffers buf{};
+  bool bound = false;
+  bool owns = false;
+  bool constructed = false;
+  // staging for the *_host entry points
+  double* act_dev = nullptr;
+  uint8_t* mask_dev = nullptr;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+int validate(const ShipEnvParams* p, long long num_envs) {
+  if (!p) return fail(SHIPENV_E_ARG, "params is NULL");
+  if (p->abi_version != SHIPENV_ABI_VERSION)
+    return fail(SHIPENV_E_ARG, "params.abi_version %d != %d", p->abi_version, SHIPENV_ABI_VERSION);
+  if (num_envs <= 0) return fail(SHIPENV_E_ARG, "num_envs must be positive");
+  if (p->env_kind < SHIPENV_ENV_COLAV_NONIW || p->env_kind > SHIPENV_ENV_RL) return fail(SHIPENV_E_ARG, "bad env_kind");
+  if (p->collav != SHIPENV_COLLAV_NONE && p->collav != SHIPENV_COLLAV_SIMPLE)
+    return fail(SHIPENV_E_ARG, "collav mode %d not supported (none=0, simple=1)", p->collav);
+  if (p->max_sampling_frequency < 0 || p->max_sampling_frequency > SHIPENV_MAX_IW)
+    return fail(SHIPENV_E_ARG, "max_sampling_frequency must be in [0, %d]", SHIPENV_MAX_IW);
+  if (p->n_poly < 0 || p->n_poly > SHIPENV_MAX_POLY) return fail(SHIPENV_E_ARG, "n_poly out of range");
+  if (p->n_poly > 0 && (p->poly_start[0] != 0 || p->poly_start[p->n_poly] > SHIPENV_MAX_VERT))
+    return fail(SHIPENV_E_ARG, "polygon vertex table out of range");
+  for (int i = 0; i < p->n_poly; ++i)
+    if (p->poly_start[i + 1] - p->poly_start[i] < 3) return fail(SHIPENV_E_ARG, "polygon %d has < 3 vertices", i);
+  if (p->ship[0].model_kind != p->ship[1].model_kind)
+    return fail(SHIPENV_E_ARG, "both ships of an environment must use the same ship model class");
+  for (int s = 0; s < 2; ++s) {
+    const ShipEnvShipParams& q = p->ship[s];
+    if (q.model_kind != SHIPENV_MODEL_SIMPLE && q.model_kind != SHIPENV_MODEL_DETAILED)
+      return fail(SHIPENV_E_ARG, "ship[%d].model_kind invalid", s);
+    if (q.n_wp < 2 || q.n_wp > SHIPENV_MAX_WP) return fail(SHIPENV_E_ARG, "ship[%d].n_wp must be in [2, %d]", s, SHIPENV_MAX_WP);
+    if (!(q.dt > 0.0) || !(q.ctrl_dt > 0.0)) return fail(SHIPENV_E_ARG, "ship[%d] time steps must be positive", s);
+    if (q.model_kind == SHIPENV_MODEL_DETAILED && !(q.dt_shaft > 0.0))
+      return fail(SHIPENV_E_ARG, "ship[%d].dt_shaft must be positive", s);
+  }
+  if (p->env_kind != SHIPENV_ENV_COLAV_NONIW && p->ship[1].n_wp + p->max_sampling_frequency > 255)
+    return fail(SHIPENV_E_ARG, "route too long");
+  return SHIPENV_OK;
+}
+
+DevView view(const shipenv* h) { return DevView{h->params_dev, h->buf, h->num_envs}; }
+
+int ship_grid(const shipenv* h) { return (int)((2 * h->num_envs + kBlock - 1) / kBlock); }
+
+int check_ready(const shipenv* h, bool need_constructed) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  if (!h->bound) return fail(SHIPENV_E_STATE, "no buffers: call shipenv_bind or shipenv_alloc first");
+  if (need_constructed && !h->constructed)
+    return fail(SHIPENV_E_STATE, "environment state not initialised: call shipenv_construct or shipenv_reset first");
+  return SHIPENV_OK;
+}
+
+template <int MODEL>
+int launch_reset(shipenv* h, const uint8_t* mask, const double* init, int do_init, int reinit, cudaStream_t st) {
+  senv::k_reset<MODEL><<<ship_grid(h), kBlock, 0, st>>>(view(h), mask, init, do_init, reinit);
+  CUDA_TRY(cudaGetLastError());
+  return SHIPENV_OK;
+}
+
+template <int MODEL, int MODE>
+int launch_env(shipenv* h, const double* actions, int k, cudaStream_t st) {
+  const int grid = ship_grid(h);
+  switch (h->params.env_kind) {
+    case SHIPENV_ENV_COLAV_NONIW:
+      senv::k_env<MODEL, SHIPENV_ENV_COLAV_NONIW, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
+      break;
+    case SHIPENV_ENV_COLAV_IW:
+      senv::k_env<MODEL, SHIPENV_ENV_COLAV_IW, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
+      break;
+    default:
+      senv::k_env<MODEL, SHIPENV_ENV_RL, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
+      break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return SHIPENV_OK;
+}
+
+int ensure_staging(shipenv* h) {
+  if (h->pinned) return SHIPENV_OK;
+  const size_t B = (size_t)h->num_envs;
+  // actions f64 | obs 8 x f32 | reward f64 | info i32 | nsub i32 | mask u8
+  h->pinned_bytes = B * (8 + 32 + 8 + 4 + 4 + 1) + 64;
+  CUDA_TRY(cudaMallocHost(&h->pinned, h->pinned_bytes));
+  CUDA_TRY(cudaMalloc(&h->act_dev, B * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&h->mask_dev, B));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  return SHIPENV_OK;
+}
+
+struct Pinned {
+  double* actions; float* obs; double* reward; int32_t* info; int32_t* nsub; uint8_t* mask;
+};
+
+Pinned pinned_view(shipenv* h) {
+  const size_t B = (size_t)h->num_envs;
+  char* p = (char*)h->pinned;
+  Pinned v;
+  v.actions = (double*)p; p += B * 8;
+  v.reward = (double*)p; p += B * 8;
+  v.obs = (float*)p; p += B * 32;
+  v.info = (int32_t*)p; p += B * 4;
+  v.nsub = (int32_t*)p; p += B * 4;
+  v.mask = (uint8_t*)p;
+  return v;
+}
+
+int fetch_outputs(shipenv* h, float* obs_host, double* reward_host, int32_t* info_host, int32_t* nsub_host) {
+  const size_t B = (size_t)h->num_envs;
+  Pinned pv = pinned_view(h);
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(pv.obs, h->buf.obs_f32, B * 32, cudaMemcpyDeviceToHost, h->stream));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(pv.reward, h->buf.reward, B * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (info_host) CUDA_TRY(cudaMemcpyAsync(pv.info, h->buf.info_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (nsub_host) CUDA_TRY(cudaMemcpyAsync(pv.nsub, h->buf.nsub_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (obs_host) memcpy(obs_host, pv.obs, B * 32);
+  if (reward_host) memcpy(reward_host, pv.reward, B * 8);
+  if (info_host) memcpy(info_host, pv.info, B * 4);
+  if (nsub_host) memcpy(nsub_host, pv.nsub, B * 4);
+  return SHIPENV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shipenv_abi_version(void) { return SHIPENV_ABI_VERSION; }
+int shipenv_sizeof_params(void) { return (int)sizeof(ShipEnvParams); }
+const char* shipenv_last_error(void) { return g_err; }
+
+int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, shipenv_t** out) {
+  if (!out) return fail(SHIPENV_E_ARG, "out is NULL");
+  *out = nullptr;
+  int rc = validate(params, num_envs);
+  if (rc) return rc;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(SHIPENV_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(SHIPENV_E_ARG, "device %d out of range [0, %d)", device, count);
+  CUDA_TRY(cudaSetDevice(device));
+  shipenv* h = new (std::nothrow) shipenv();
+  if (!h) return fail(SHIPENV_E_NOMEM, "out of host memory");
+  h->device = device;
+  h->num_envs = num_envs;
+  h->params = *params;
+  cudaError_t ce = cudaMalloc(&h->params_dev, sizeof(ShipEnvParams));
+  if (ce == cudaSuccess) ce = cudaMemcpy(h->params_dev, params, sizeof(ShipEnvParams), cudaMemcpyHostToDevice);
+  if (ce != cudaSuccess) {
+    delete h;
+    return fail(SHIPENV_E_CUDA, "uploading parameters: %s", cudaGetErrorString(ce));
+  }
+  *out = h;
+  return SHIPENV_OK;
+}
+
+int shipenv_destroy(shipenv_t* h) {
+  if (!h) return SHIPENV_OK;
+  cudaSetDevice(h->device);
+  if (h->owns) {
+    cudaFree(h->buf.ship_f64); cudaFree(h->buf.ship_i32); cudaFree(h->buf.env_f64); cudaFree(h->buf.env_i32);
+    cudaFree(h->buf.iw_f64); cudaFree(h->buf.prev_f32); cudaFree(h->buf.obs_f32); cudaFree(h->buf.reward);
+    cudaFree(h->buf.info_i32); cudaFree(h->buf.nsub_i32); cudaFree(h->buf.counters);
+  }
+  cudaFree(h->params_dev);
+  cudaFree(h->act_dev);
+  cudaFree(h->mask_dev);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return SHIPENV_OK;
+}
+
+int shipenv_layout(const shipenv_t* h, ShipEnvLayout* out) {
+  if (!h || !out) return fail(SHIPENV_E_ARG, "NULL argument");
+  const int64_t B = h->num_envs;
+  out->ship_f64 = (int64_t)SHIPENV_SF_COUNT * 2 * B;
+  out->ship_i32 = 2 * B;
+  out->env_f64 = (int64_t)SHIPENV_EF_COUNT * B;
+  out->env_i32 = (int64_t)SHIPENV_EI_COUNT * B;
+  out->iw_f64 = (int64_t)2 * SHIPENV_MAX_IW * B;
+  out->prev_f32 = 4 * B;
+  out->obs_f32 = 8 * B;
+  out->reward = B;
+  out->info_i32 = B;
+  out->nsub_i32 = B;
+  out->counters = 4;
+  return SHIPENV_OK;
+}
+
+int shipenv_bind(shipenv_t* h, const ShipEnvBuffers* b) {
+  if (!h || !b) return fail(SHIPENV_E_ARG, "NULL argument");
+  if (h->owns) return fail(SHIPENV_E_STATE, "buffers already allocated by shipenv_alloc");
+  if (!b->ship_f64 || !b->ship_i32 || !b->env_f64 || !b->env_i32 || !b->iw_f64 || !b->prev_f32 || !b->obs_f32 ||
+      !b->reward || !b->info_i32 || !b->nsub_i32)
+    return fail(SHIPENV_E_ARG, "every buffer except counters must be non-NULL");
+  if (((uintptr_t)b->obs_f32) % 16) return fail(SHIPENV_E_ARG, "obs_f32 must be 16-byte aligned");
+  h->buf = *b;
+  h->bound = true;
+  h->constructed = false;
+  return SHIPENV_OK;
+}
+
+int shipenv_alloc(shipenv_t* h) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  if (h->bound) return fail(SHIPENV_E_STATE, "buffers already bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  ShipEnvLayout L;
+  shipenv_layout(h, &L);
+  CUDA_TRY(cudaMalloc(&h->buf.ship_f64, L.ship_f64 * 8));
+  CUDA_TRY(cudaMalloc(&h->buf.ship_i32, L.ship_i32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.env_f64, L.env_f64 * 8));
+  CUDA_TRY(cudaMalloc(&h->buf.env_i32, L.env_i32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.iw_f64, L.iw_f64 * 8));
+  CUDA_TRY(cudaMalloc(&h->buf.prev_f32, L.prev_f32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.obs_f32, L.obs_f32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.reward, L.reward * 8));
+  CUDA_TRY(cudaMalloc(&h->buf.info_i32, L.info_i32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.nsub_i32, L.nsub_i32 * 4));
+  CUDA_TRY(cudaMalloc(&h->buf.counters, L.counters * 8));
+  CUDA_TRY(cudaMemset(h->buf.counters, 0, L.counters * 8));
+  CUDA_TRY(cudaMemset(h->buf.iw_f64, 0, L.iw_f64 * 8));
+  h->bound = true;
+  h->owns = true;
+  return SHIPENV_OK;
+}
+
+int shipenv_buffers(const shipenv_t* h, ShipEnvBuffers* out) {
+  if (!h || !out) return fail(SHIPENV_E_ARG, "NULL argument");
+  if (!h->bound) return fail(SHIPENV_E_STATE, "no buffers bound");
+  *out = h->buf;
+  return SHIPENV_OK;
+}
+
+int shipenv_set_params(shipenv_t* h, const ShipEnvParams* params) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  int rc = validate(params, h->num_envs);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->params = *params;
+  CUDA_TRY(cudaDeviceSynchronize());   // kernels in flight on any stream may still read the old block
+  CUDA_TRY(cudaMemcpy(h->params_dev, params, sizeof(ShipEnvParams), cudaMemcpyHostToDevice));
+  return SHIPENV_OK;
+}
+
+int shipenv_construct(shipenv_t* h, const double* init_dev, void* stream) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+           ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, nullptr, init_dev, 0, 1, st)
+           : launch_reset<SHIPENV_MODEL_DETAILED>(h, nullptr, init_dev, 0, 1, st);
+  if (rc) return rc;
+  senv::k_init_prev_states<<<(int)((h->num_envs + 255) / 256), 256, 0, st>>>(view(h));
+  CUDA_TRY(cudaGetLastError());
+  h->constructed = true;
+  return SHIPENV_OK;
+}
+
+int shipenv_reset(shipenv_t* h, const uint8_t* mask_dev, const double* init_dev, void* stream) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  if (!h->constructed) {
+    if (mask_dev) return fail(SHIPENV_E_STATE, "the first reset must cover all environments (mask = NULL)");
+    rc = shipenv_construct(h, init_dev, stream);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+             ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, mask_dev, init_dev, 1, 1, st)
+             : launch_reset<SHIPENV_MODEL_DETAILED>(h, mask_dev, init_dev, 1, 1, st);
+}
+
+int shipenv_init_step(shipenv_t* h, void* stream) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+             ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, nullptr, nullptr, 1, 0, st)
+             : launch_reset<SHIPENV_MODEL_DETAILED>(h, nullptr, nullptr, 1, 0, st);
+}
+
+int shipenv_step(shipenv_t* h, const double* actions_dev, void* stream) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  if (h->params.env_kind == SHIPENV_ENV_COLAV_NONIW)
+    return fail(SHIPENV_E_STATE, "step(action) needs an intermediate-waypoint env kind (COLAV_IW or RL)");
+  if (!actions_dev) return fail(SHIPENV_E_ARG, "actions_dev is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+             ? launch_env<SHIPENV_MODEL_SIMPLE, senv::MODE_STEP>(h, actions_dev, 0, st)
+             : launch_env<SHIPENV_MODEL_DETAILED, senv::MODE_STEP>(h, actions_dev, 0, st);
+}
+
+int shipenv_substeps(shipenv_t* h, int k, void* stream) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  if (k < 0) return fail(SHIPENV_E_ARG, "k must be >= 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+             ? launch_env<SHIPENV_MODEL_SIMPLE, senv::MODE_SUBSTEPS>(h, nullptr, k, st)
+             : launch_env<SHIPENV_MODEL_DETAILED, senv::MODE_SUBSTEPS>(h, nullptr, k, st);
+}
+
+int shipenv_ship_rollout(shipenv_t* h, int k, void* stream) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  if (k < 0) return fail(SHIPENV_E_ARG, "k must be >= 0");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
+    senv::k_ship_rollout<SHIPENV_MODEL_SIMPLE><<<ship_grid(h), kBlock, 0, st>>>(view(h), k);
+  else
+    senv::k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(h), kBlock, 0, st>>>(view(h), k);
+  CUDA_TRY(cudaGetLastError());
+  return SHIPENV_OK;
+}
+
+int shipenv_reset_host(shipenv_t* h, const uint8_t* mask_host, float* obs_host) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  const uint8_t* mask_dev = nullptr;
+  if (mask_host) {
+    Pinned pv = pinned_view(h);
+    memcpy(pv.mask, mask_host, (size_t)h->num_envs);
+    CUDA_TRY(cudaMemcpyAsync(h->mask_dev, pv.mask, (size_t)h->num_envs, cudaMemcpyHostToDevice, h->stream));
+    mask_dev = h->mask_dev;
+  }
+  rc = shipenv_reset(h, mask_dev, nullptr, h->stream);
+  if (rc) return rc;
+  return fetch_outputs(h, obs_host, nullptr, nullptr, nullptr);
+}
+
+int shipenv_step_host(shipenv_t* h, const double* actions_host, float* obs_host, double* reward_host,
+                      int32_t* info_host, int32_t* nsub_host) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  if (!actions_host) return fail(SHIPENV_E_ARG, "actions_host is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  Pinned pv = pinned_view(h);
+  memcpy(pv.actions, actions_host, (size_t)h->num_envs * 8);
+  CUDA_TRY(cudaMemcpyAsync(h->act_dev, pv.actions, (size_t)h->num_envs * 8, cudaMemcpyHostToDevice, h->stream));
+  rc = shipenv_step(h, h->act_dev, h->stream);
+  if (rc) return rc;
+  return fetch_outputs(h, obs_host, reward_host, info_host, nsub_host);
+}
+
+int shipenv_substeps_host(shipenv_t* h, int k, float* obs_host, double* reward_host, int32_t* info_host,
+                          int32_t* nsub_host) {
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  rc = ensure_staging(h);
+  if (rc) return rc;
+  rc = shipenv_substeps(h, k, h->stream);
+  if (rc) return rc;
+  return fetch_outputs(h, obs_host, reward_host, info_host, nsub_host);
+}
+
+int shipenv_read_counters(shipenv_t* h, unsigned long long* out_host) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  if (!out_host) return fail(SHIPENV_E_ARG, "out_host is NULL");
+  if (!h->buf.counters) return fail(SHIPENV_E_STATE, "no counters buffer bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaMemcpy(out_host, h->buf.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SHIPENV_OK;
+}
+
+int shipenv_measure_fp64_peak(int device, int repeats, double* tflops_out) {
+  if (!tflops_out) return fail(SHIPENV_E_ARG, "tflops_out is NULL");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  double* out = nullptr;
+  CUDA_TRY(cudaMalloc(&out, 8));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  const int iters = 1 << 16, threads = 256, blocks = prop.multiProcessorCount * 8;
+  double best_ms = 1e30;
+  if (repeats < 1) repeats = 1;
+  for (int r = 0; r < repeats + 1; ++r) {          // first launch is the warm-up
+    CUDA_TRY(cudaEventRecord(e0));
+    senv::k_dfma_peak<<<blocks, threads>>>(out, iters, 0.9999999, 1e-7);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  const double flops = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+  *tflops_out = flops / (best_ms * 1e-3) / 1e12;
+  return SHIPENV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,848 @@
+// shipenv_kernels.cuh -- sm_100a device code of the batched ship-in-transit environment.
+//
+// Execution model: one ship asset per thread, lane pairs (2e, 2e+1) = (ship under test, obstacle
+// ship) of environment e.  A lane keeps its ship's whole state in registers (6 hull states, shaft
+// speed, clock, LOS and controller integrators, the current route segment) for as many simulator
+// steps as the call needs; the two ships of an environment only meet in the reward/termination
+// evaluation, which exchanges a handful of values with __shfl_xor_sync(.., 1).  Ship-type constants,
+// the fixed routes and the map polygons are staged once per CTA in shared memory; per-ship and
+// per-env state is structure-of-arrays in HBM (include/shipenv.h) so every load/store of a warp is
+// one contiguous 256-byte (FP64) or 128-byte (int32) segment.
+//
+// Arithmetic is IEEE FP64 with the reference's forward-Euler scheme and operation order; the file is
+// compiled with -fmad=false so a*b+c is two roundings, as in CPython/NumPy.
+// Citations are paths relative to the reference root.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "shipenv.h"
+
+namespace senv {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr double kPi = 3.141592653589793;
+
+struct DevView {
+  const ShipEnvParams* params;
+  ShipEnvBuffers buf;
+  long long num_envs;
+};
+
+enum Mode { MODE_STEP = 0, MODE_SUBSTEPS = 1 };
+
+// ------------------------------------------------------------------------------------------------
+// registers of one ship
+// ------------------------------------------------------------------------------------------------
+struct Ship {
+  double north, east, yaw, u, v, r, omega, time;
+  double e_ct, e_ct_int;
+  double hdg_err_i, hdg_prev_err, spd_err_i, spd_aux;
+  // current LOS segment (wp[k-1] -> wp[k]) and its bearing
+  double pn, pe, wn, we, alpha, sin_a, cos_a;
+  int k;          // next waypoint index
+  int n_wp;       // route length (file waypoints + sampled intermediate waypoints)
+  int stop;
+};
+
+struct Route {            // route of this lane: fixed file waypoints + per-env sampled waypoints
+  const double* file_n;   // shared memory
+  const double* file_e;
+  const double* iw_n;     // global, stride num_envs; nullptr when the route is fixed
+  const double* iw_e;
+  long long stride;
+  int n_file;
+};
+
+__device__ __forceinline__ void route_wp(const Route& rt, int n_iw, int idx, double& n, double& e) {
+  // list.insert(-1, .) keeps the file's last waypoint last (controllers.py:417-422)
+  const int head = rt.n_file - 1;
+  if (idx < head) { n = rt.file_n[idx]; e = rt.file_e[idx]; }
+  else if (idx < head + n_iw) { n = rt.iw_n[(long long)(idx - head) * rt.stride]; e = rt.iw_e[(long long)(idx - head) * rt.stride]; }
+  else { n = rt.file_n[head]; e = rt.file_e[head]; }
+}
+
+__device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship& s) {
+  route_wp(rt, n_iw, s.k - 1, s.pn, s.pe);
+  route_wp(rt, n_iw, s.k, s.wn, s.we);
+  const double dx = s.wn - s.pn, dy = s.we - s.pe;
+  s.alpha = atan2(dy, dx);                                   // LOS_guidance.py:105-107
+  sincos(s.alpha, &s.sin_a, &s.cos_a);
+}
+
+__device__ __forceinline__ double sat(double val, double low, double hi) {   // controllers.py:67-72
+  const double m = (hi < val) ? hi : val;
+  return (m > low) ? m : low;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one simulator step of one ship: autopilot (LOS + heading PID), speed controller, hull + machinery
+// derivatives, forward Euler.  SURVEY.md Appendix A; ship_model.py:351-416, rl_env ship_model.py:
+// 834-901, ship_engine.py:403-443, controllers.py:106-125,183-189,286-295,425-433,
+// LOS_guidance.py:83-117, utils.py:42-53.
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
+                                          bool collav_hit, double collav_bias) {
+  // --- NavigationSystem.next_wpt
+  {
+    const double dn = s.wn - s.north, de = s.we - s.east;
+    if (dn * dn + de * de <= P.los_ra * P.los_ra) {
+      if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
+    }
+  }
+  // --- NavigationSystem.los_guidance
+  double e_ct = -(s.north - s.pn) * s.sin_a + (s.east - s.pe) * s.cos_a;
+  const double R = P.los_r;
+  if (e_ct * e_ct >= R * R) e_ct = 0.99 * R;
+  s.e_ct = e_ct;
+  double delta = sqrt(R * R - e_ct * e_ct);
+  if (!(delta > 1e-6)) delta = 1e-6;
+  const double q = e_ct / delta;
+  if (fabs(s.e_ct_int + q) <= P.los_limit) s.e_ct_int += q;
+  const double chi_r = atan(-q - s.e_ct_int * P.los_ki);
+  const double heading_ref = s.alpha + chi_r;
+  // --- heading PID -> rudder angle
+  double rudder;
+  {
+    const double error = (heading_ref + (-0.0)) - s.yaw;
+    const double d_error = (error - s.hdg_prev_err) / P.ctrl_dt;
+    const double error_i = s.hdg_err_i + error * P.ctrl_dt;
+    s.hdg_prev_err = error;
+    s.hdg_err_i = error_i;
+    const double out = error * P.hdg_kp + d_error * P.hdg_kd + error_i * P.hdg_ki;
+    rudder = sat(-out, -P.max_rudder, P.max_rudder);
+  }
+  // --- speed controller
+  double cmd;
+  if (MODEL == SHIPENV_MODEL_SIMPLE) {
+    const double error = P.desired_speed - s.u;
+    const double d_error = (error - s.spd_aux) / P.ctrl_dt;
+    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    s.spd_aux = error;
+    s.spd_err_i = error_i;
+    const double out = error * P.spd_kp + d_error * P.spd_kd + error_i * P.spd_ki;
+    cmd = sat(out, -P.max_thrust, P.max_thrust);
+  } else {
+    const double error = P.desired_speed - s.u;
+    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    s.spd_err_i = error_i;
+    const double w_d = sat(error * P.kp_ship_speed + error_i * P.ki_ship_speed, 0.0, P.max_shaft_speed);
+    // measured_shaft_speed = forward_speed (rl_env env.py:397-401)
+    const double error2 = w_d - s.u;
+    const double error2_i = s.spd_aux + error2 * P.ctrl_dt;
+    s.spd_aux = error2_i;
+    cmd = sat(error2 * P.kp_shaft_speed + error2_i * P.ki_shaft_speed, 0.0, 1.1);
+  }
+  // --- collav 'simple' (run_colav env.py:1189-1202, rl_env env.py:405-418)
+  if (collav_hit) {
+    cmd *= 0.5;
+    cmd = (cmd < 0.0) ? 0.0 : ((cmd > 1.1) ? 1.1 : cmd);
+    rudder += collav_bias;
+    rudder = (rudder < -P.max_rudder) ? -P.max_rudder : ((rudder > P.max_rudder) ? P.max_rudder : rudder);
+  }
+  // --- kinematics
+  double spsi, cpsi;
+  sincos(s.yaw, &spsi, &cpsi);
+  const double u = s.u, v = s.v, r = s.r;
+  const double d_north = cpsi * u + (-spsi) * v;
+  const double d_east = spsi * u + cpsi * v;
+  // --- machinery
+  double thrust, d_omega = 0.0;
+  if (MODEL == SHIPENV_MODEL_SIMPLE) {
+    thrust = cmd;
+  } else {
+    const double w = s.omega;
+    const double a_me = cmd * P.p_me / (w + 0.1);
+    const double tq_me = (P.tq_me_max < a_me) ? P.tq_me_max : a_me;
+    const double a_el = cmd * P.p_el / (w + 0.1);
+    const double tq_el = (P.tq_el_max < a_el) ? P.tq_el_max : a_el;
+    const double eq_me = (tq_me - P.d_me * w) / P.r_me;
+    const double eq_hsg = (tq_el - P.d_hsg * w) / P.r_hsg;
+    d_omega = (eq_me + eq_hsg - P.k_torque * (w * w)) / P.jp;
+    thrust = P.thrust_coeff * w * fabs(w);
+  }
+  // --- current in the body frame, rudder forces
+  const double u_c = cpsi * P.cur_n + spsi * P.cur_e;
+  const double v_c = (-spsi) * P.cur_n + cpsi * P.cur_e;
+  const double u_r = u - u_c, v_r = v - v_c;
+  const double f_rudder_v = -P.c_rudder_v * rudder * (u - u_c);
+  const double f_rudder_r = -P.c_rudder_r * rudder * (u - u_c);
+  // --- wind
+  double sw, cw;
+  sincos(P.wind_dir - s.yaw, &sw, &cw);
+  const double u_rw = P.wind_speed * cw - u;
+  const double v_rw = P.wind_speed * sw - v;
+  const double gamma_rw = -atan2(v_rw, u_rw);
+  const double wind_rw2 = u_rw * u_rw + v_rw * v_rw;
+  double sg, cg;
+  sincos(gamma_rw, &sg, &cg);
+  const double c_x = -0.5 * cg;
+  const double c_y = 0.7 * sg;
+  const double c_n = 0.08 * sin(2 * gamma_rw);
+  const double tau_coeff = 0.5 * 1.2 * wind_rw2;
+  const double tau_u = tau_coeff * c_x * P.proj_area_f;
+  const double tau_v = tau_coeff * c_y * P.proj_area_l;
+  const double tau_n = tau_coeff * c_n * P.proj_area_l * P.l_ship;
+  // --- kinetics (x_g = 0, diagonal mass matrix)
+  const double m = P.mass;
+  const double crb0 = (-m * v) * r;
+  const double crb1 = (m * u) * r;
+  const double crb2 = (m * v) * u + (-m * u) * v;
+  const double ca0 = (P.y_dv * v_r) * r;
+  const double ca1 = (-P.x_du * u_r) * r;
+  const double ca2 = (-P.y_dv * v_r) * u_r + (P.x_du * u_r) * v_r;
+  const double dmp0 = (P.lin_damp_u + P.ku * u) * u_r;
+  const double dmp1 = (P.lin_damp_v + P.kv * v) * v_r;
+  const double dmp2 = (P.lin_damp_r + P.kr * r) * r;
+  const double f0 = -crb0 - ca0 - dmp0 + tau_u + 0.0 + thrust;
+  const double f1 = -crb1 - ca1 - dmp1 + tau_v + 0.0 + f_rudder_v;
+  const double f2 = -crb2 - ca2 - dmp2 + tau_n + 0.0 + f_rudder_r;
+  const double d_u = P.inv_m_u * f0;
+  const double d_v = P.inv_m_v * f1;
+  const double d_r = P.inv_m_r * f2;
+  // --- forward Euler
+  const double dt = P.dt;
+  s.north = s.north + d_north * dt;
+  s.east = s.east + d_east * dt;
+  s.yaw = s.yaw + r * dt;
+  s.u = s.u + d_u * dt;
+  s.v = s.v + d_v * dt;
+  s.r = s.r + d_r * dt;
+  if (MODEL == SHIPENV_MODEL_DETAILED) s.omega = s.omega + d_omega * P.dt_shaft;
+  s.time = s.time + dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// map geometry (obstacle.py:126-141, check_condition.py:16-119); Shapely semantics: contains() is the
+// strict interior (even-odd rule), exterior.distance() the distance to the closed ring.
+// ------------------------------------------------------------------------------------------------
+struct MapView {
+  const double* ve;
+  const double* vn;
+  const int* start;
+  const double* bbox;   // [n_poly][4] = min_e, max_e, min_n, max_n (shared memory)
+  int n_poly;
+};
+
+__device__ __forceinline__ bool map_contains(const MapView& mp, double n_pos, double e_pos) {
+  const double x = e_pos, y = n_pos;
+  for (int p = 0; p < mp.n_poly; ++p) {
+    const double* bb = mp.bbox + 4 * p;
+    // a point outside the polygon's bounding box crosses an even number of edges: skip (exact)
+    if (x < bb[0] || x > bb[1] || y < bb[2] || y > bb[3]) continue;
+    const int a = mp.start[p], b = mp.start[p + 1];
+    bool inside = false;
+    double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
+    for (int i = a; i < b; ++i) {
+      const double xi = mp.ve[i], yi = mp.vn[i];
+      if ((yi > y) != (yj > y)) {
+        if (x < (xj - xi) * (y - yi) / (yj - yi) + xi) inside = !inside;
+      }
+      xj = xi; yj = yi;
+    }
+    if (inside) return true;
+  }
+  return false;
+}
+
+// min over polygons of ring distance; only its value when <= clip matters to the caller
+// (reward_function.py:386-389, 454-457), so polygons whose bounding box is farther than clip are
+// skipped (exact: they cannot hold the minimum if the minimum is <= clip).
+__device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, double e_pos, double clip) {
+  const double px = e_pos, py = n_pos;
+  double best2 = INFINITY;
+  for (int p = 0; p < mp.n_poly; ++p) {
+    const double* bb = mp.bbox + 4 * p;
+    const double ddx = fmax(fmax(bb[0] - px, px - bb[1]), 0.0);
+    const double ddy = fmax(fmax(bb[2] - py, py - bb[3]), 0.0);
+    if (ddx > clip + 1.0 || ddy > clip + 1.0) continue;
+    const int a = mp.start[p], b = mp.start[p + 1];
+    for (int i = a; i < b; ++i) {
+      const int k = (i + 1 < b) ? i + 1 : a;
+      const double ax = mp.ve[i], ay = mp.vn[i], bx = mp.ve[k], by = mp.vn[k];
+      const double dx = bx - ax, dy = by - ay;
+      const double l2 = dx * dx + dy * dy;
+      double t = 0.0;
+      if (l2 != 0.0) {
+        t = ((px - ax) * dx + (py - ay) * dy) / l2;
+        t = (t < 1.0) ? t : 1.0;
+        t = (t > 0.0) ? t : 0.0;
+      }
+      const double cx = ax + t * dx, cy = ay + t * dy;
+      const double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
+      best2 = (d2 < best2) ? d2 : best2;
+    }
+  }
+  return sqrt(best2);   // sqrt is monotonic and correctly rounded: sqrt(min d2) == min sqrt(d2)
+}
+
+__device__ __forceinline__ bool pos_inside_obstacles(const MapView& mp, double n, double e, double ship_length) {
+  const double margin = ship_length / 2;
+  const double mn = n - margin, me = e - margin, xn = n + margin, xe = e + margin;
+  return map_contains(mp, mn, me) || map_contains(mp, mn, xe) || map_contains(mp, xn, me) || map_contains(mp, xn, xe);
+}
+
+__device__ __forceinline__ double py_mod(double a, double b) {   // Python / NumPy float modulo
+  double m = fmod(a, b);
+  if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
+  else m = copysign(0.0, b);
+  return m;
+}
+
+__device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
+  return __shfl_xor_sync(FULL_MASK, v, lane_mask);
+}
+
+// shared-memory staging of the parameter block
+struct SharedBlock {
+  ShipEnvParams p;
+  double bbox[SHIPENV_MAX_POLY * 4];
+};
+
+__device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
+  const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sb.p);
+  constexpr int words = sizeof(ShipEnvParams) / 8;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  for (int p = threadIdx.x; p < sb.p.n_poly; p += blockDim.x) {
+    double mne = INFINITY, mxe = -INFINITY, mnn = INFINITY, mxn = -INFINITY;
+    for (int i = sb.p.poly_start[p]; i < sb.p.poly_start[p + 1]; ++i) {
+      mne = fmin(mne, sb.p.vert_e[i]); mxe = fmax(mxe, sb.p.vert_e[i]);
+      mnn = fmin(mnn, sb.p.vert_n[i]); mxn = fmax(mxn, sb.p.vert_n[i]);
+    }
+    sb.bbox[4 * p + 0] = mne; sb.bbox[4 * p + 1] = mxe; sb.bbox[4 * p + 2] = mnn; sb.bbox[4 * p + 3] = mxn;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void load_ship(const DevView& dv, long long n_ships, long long sidx, Ship& s) {
+  const double* f = dv.buf.ship_f64;
+  s.north = f[SHIPENV_SF_NORTH * n_ships + sidx];
+  s.east = f[SHIPENV_SF_EAST * n_ships + sidx];
+  s.yaw = f[SHIPENV_SF_YAW * n_ships + sidx];
+  s.u = f[SHIPENV_SF_U * n_ships + sidx];
+  s.v = f[SHIPENV_SF_V * n_ships + sidx];
+  s.r = f[SHIPENV_SF_R * n_ships + sidx];
+  s.omega = f[SHIPENV_SF_OMEGA * n_ships + sidx];
+  s.time = f[SHIPENV_SF_TIME * n_ships + sidx];
+  s.e_ct = f[SHIPENV_SF_E_CT * n_ships + sidx];
+  s.e_ct_int = f[SHIPENV_SF_E_CT_INT * n_ships + sidx];
+  s.hdg_err_i = f[SHIPENV_SF_HDG_ERR_I * n_ships + sidx];
+  s.hdg_prev_err = f[SHIPENV_SF_HDG_PREV_ERR * n_ships + sidx];
+  s.spd_err_i = f[SHIPENV_SF_SPD_ERR_I * n_ships + sidx];
+  s.spd_aux = f[SHIPENV_SF_SPD_AUX * n_ships + sidx];
+  const int packed = dv.buf.ship_i32[sidx];
+  s.k = packed & 0xff;
+  s.stop = (packed >> 8) & 1;
+}
+
+__device__ __forceinline__ void store_ship(const DevView& dv, long long n_ships, long long sidx, const Ship& s) {
+  double* f = dv.buf.ship_f64;
+  f[SHIPENV_SF_NORTH * n_ships + sidx] = s.north;
+  f[SHIPENV_SF_EAST * n_ships + sidx] = s.east;
+  f[SHIPENV_SF_YAW * n_ships + sidx] = s.yaw;
+  f[SHIPENV_SF_U * n_ships + sidx] = s.u;
+  f[SHIPENV_SF_V * n_ships + sidx] = s.v;
+  f[SHIPENV_SF_R * n_ships + sidx] = s.r;
+  f[SHIPENV_SF_OMEGA * n_ships + sidx] = s.omega;
+  f[SHIPENV_SF_TIME * n_ships + sidx] = s.time;
+  f[SHIPENV_SF_E_CT * n_ships + sidx] = s.e_ct;
+  f[SHIPENV_SF_E_CT_INT * n_ships + sidx] = s.e_ct_int;
+  f[SHIPENV_SF_HDG_ERR_I * n_ships + sidx] = s.hdg_err_i;
+  f[SHIPENV_SF_HDG_PREV_ERR * n_ships + sidx] = s.hdg_prev_err;
+  f[SHIPENV_SF_SPD_ERR_I * n_ships + sidx] = s.spd_err_i;
+  f[SHIPENV_SF_SPD_AUX * n_ships + sidx] = s.spd_aux;
+  dv.buf.ship_i32[sidx] = (s.k & 0xff) | (s.stop << 8);
+}
+
+__device__ __forceinline__ void init_ship_regs(const ShipEnvShipParams& P, const double* init_dev, long long n_ships,
+                                               long long sidx, Ship& s) {
+  // BaseShipModel.__init__ / reset (ship_model.py:100-118, 303-316), controller resets
+  // (controllers.py:82-90,141-151), NavigationSystem.reset (LOS_guidance.py:129-136)
+  if (init_dev) {
+    s.north = init_dev[0 * n_ships + sidx]; s.east = init_dev[1 * n_ships + sidx];
+    s.yaw = init_dev[2 * n_ships + sidx]; s.u = init_dev[3 * n_ships + sidx];
+    s.v = init_dev[4 * n_ships + sidx]; s.r = init_dev[5 * n_ships + sidx];
+    s.omega = init_dev[6 * n_ships + sidx];
+  } else {
+    s.north = P.init_north; s.east = P.init_east; s.yaw = P.init_yaw;
+    s.u = P.init_u; s.v = P.init_v; s.r = P.init_r; s.omega = P.init_omega;
+  }
+  s.time = 0.0;
+  s.e_ct = 0.0; s.e_ct_int = 0.0;
+  s.hdg_err_i = 0.0; s.hdg_prev_err = 0.0;
+  s.spd_err_i = 0.0;
+  s.spd_aux = (P.model_kind == SHIPENV_MODEL_DETAILED) ? P.init_shaft_err_i : 0.0;
+  s.k = 1;
+  s.n_wp = P.n_wp;
+  s.stop = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// construct / reset (+ init_step) kernel
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__ init_dev, int do_init_step,
+        int reinit) {
+  __shared__ SharedBlock sb;
+  stage_params(sb, dv.params);
+  const long long n_ships = 2 * dv.num_envs;
+  const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= n_ships) return;
+  const long long env = sidx >> 1;
+  const int role = (int)(sidx & 1);
+  if (mask && !mask[env]) return;
+  const ShipEnvShipParams& P = sb.p.ship[role];
+  const bool dynamic_route = (role == 1) && (sb.p.env_kind != SHIPENV_ENV_COLAV_NONIW);
+  Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
+           dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * dv.num_envs + env : nullptr, dv.num_envs, P.n_wp};
+  Ship s;
+  if (reinit) {
+    init_ship_regs(P, init_dev, n_ships, sidx, s);
+    // obs rows <- initial_states (env.py:107-110); built from both ships of the pair
+    float* orow = dv.buf.obs_f32 + env * 8;
+    if (role == 0) { orow[0] = (float)s.north; orow[1] = (float)s.east; orow[2] = 0.0f; }
+    else { orow[3] = (float)s.north; orow[4] = (float)s.east; orow[5] = (float)s.yaw; orow[6] = 0.0f; orow[7] = (float)s.u; }
+    if (role == 1) {
+      // init_get_intermediate_waypoints + results snapshot (env.py:143-184)
+      double* ef = dv.buf.env_f64;
+      ef[SHIPENV_EF_TRAVEL_DIST * dv.num_envs + env] = 0.0;
+      ef[SHIPENV_EF_TRAVEL_TIME * dv.num_envs + env] = 0.0;
+      ef[SHIPENV_EF_ACC_REWARD * dv.num_envs + env] = 0.0;
+      ef[SHIPENV_EF_N_BASE * dv.num_envs + env] = sb.p.n_base0;
+      ef[SHIPENV_EF_E_BASE * dv.num_envs + env] = sb.p.e_base0;
+      ef[SHIPENV_EF_LOG_NORTH * dv.num_envs + env] = s.north;
+      ef[SHIPENV_EF_LOG_EAST * dv.num_envs + env] = s.east;
+      int* ei = dv.buf.env_i32;
+      ei[SHIPENV_EI_SAMPLING_COUNT * dv.num_envs + env] = 0;
+      ei[SHIPENV_EI_SNAPSHOT_INFO * dv.num_envs + env] = 0;
+      ei[SHIPENV_EI_FLAGS * dv.num_envs + env] = 0;
+      dv.buf.reward[env] = 0.0;
+      dv.buf.info_i32[env] = 0;
+      dv.buf.nsub_i32[env] = 0;
+    }
+  } else {
+    load_ship(dv, n_ships, sidx, s);
+    s.n_wp = P.n_wp + (dynamic_route ? dv.buf.env_i32[SHIPENV_EI_SAMPLING_COUNT * dv.num_envs + env] : 0);
+  }
+  if (do_init_step) {
+    // init_step (env.py:297-342): controllers, log row, one integration step, tracker on
+    refresh_segment(rt, 0, s);
+    if (role == 1) {
+      dv.buf.env_f64[SHIPENV_EF_LOG_NORTH * dv.num_envs + env] = s.north;
+      dv.buf.env_f64[SHIPENV_EF_LOG_EAST * dv.num_envs + env] = s.east;
+      dv.buf.env_i32[SHIPENV_EI_FLAGS * dv.num_envs + env] |= SHIPENV_FLAG_TRACKER;
+    }
+    ship_step<MODEL>(P, rt, 0, s, false, 0.0);
+  }
+  store_ship(dv, n_ships, sidx, s);
+}
+
+// self.states is float32 and is only (re)initialised by __init__ (env.py:110): separate kernel so
+// that reset() leaves it alone.
+__global__ void k_init_prev_states(DevView dv) {
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= dv.num_envs) return;
+  const float* orow = dv.buf.obs_f32 + env * 8;
+  dv.buf.prev_f32[0 * dv.num_envs + env] = orow[0];
+  dv.buf.prev_f32[1 * dv.num_envs + env] = orow[1];
+  dv.buf.prev_f32[2 * dv.num_envs + env] = orow[3];
+  dv.buf.prev_f32[3 * dv.num_envs + env] = orow[4];
+}
+
+// ------------------------------------------------------------------------------------------------
+// the env kernel: step(action) [MODE_STEP] or k x _step() [MODE_SUBSTEPS]
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int ENVKIND, int MODE>
+__global__ void __launch_bounds__(128)
+k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
+  __shared__ SharedBlock sb;
+  stage_params(sb, dv.params);
+  const ShipEnvParams& G = sb.p;
+  const long long B = dv.num_envs;
+  const long long n_ships = 2 * B;
+  const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = sidx < n_ships;
+  const long long env = valid ? (sidx >> 1) : 0;
+  const int role = (int)(threadIdx.x & 1);
+  const ShipEnvShipParams& P = G.ship[role];
+  constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
+  constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
+  const bool dynamic_route = IS_IW && role == 1;
+  const Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
+                 dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * B + env : nullptr, B, P.n_wp};
+  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, G.n_poly};
+  const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
+  const bool collav_lane = (G.collav == SHIPENV_COLLAV_SIMPLE) && (role == 0 || !IS_IW);
+  const double collav_bias = IS_RL ? (-15.0 * (kPi / 180.0)) : (15.0 * (kPi / 180.0));
+  const double route_end_n = P.wp_north[P.n_wp - 1], route_end_e = P.wp_east[P.n_wp - 1];
+
+  Ship s;
+  double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0, n_base = 0.0, e_base = 0.0;
+  double log_n = 0.0, log_e = 0.0;
+  int sampling_count = 0, snapshot_info = 0, flags = 0;
+  float ps_tn = 0.f, ps_te = 0.f, ps_on = 0.f, ps_oe = 0.f;
+  bool finished = true;
+  if (valid) {
+    load_ship(dv, n_ships, sidx, s);
+    const double* ef = dv.buf.env_f64;
+    travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
+    travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
+    acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
+    n_base = ef[SHIPENV_EF_N_BASE * B + env];
+    e_base = ef[SHIPENV_EF_E_BASE * B + env];
+    log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
+    log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+    const int* ei = dv.buf.env_i32;
+    sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
+    snapshot_info = ei[SHIPENV_EI_SNAPSHOT_INFO * B + env];
+    flags = ei[SHIPENV_EI_FLAGS * B + env];
+    if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+      ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
+      ps_on = dv.buf.prev_f32[2 * B + env]; ps_oe = dv.buf.prev_f32[3 * B + env];
+    }
+    finished = (flags & SHIPENV_FLAG_DONE) != 0;
+  } else {
+    s = Ship{};
+    s.k = 1;
+  }
+  int n_iw = dynamic_route ? sampling_count : 0;
+  s.n_wp = P.n_wp + n_iw;
+
+  // outputs of this call
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f;      // this lane's next_states entries
+  double out_reward = 0.0;
+  int out_info = 0, nsub = 0;
+  bool have_obs = false;      // next_observations was assigned by this call
+  bool write_snapshot_only = false;
+  int stage = 0;              // MODE_STEP: 0 main loop, 1 extra step after RoA, 2 run to completion
+  bool have_iw = false;
+  int k_left = k_substeps;
+
+  if (MODE == MODE_STEP && !finished) {
+    // ---------------- step(action) prologue: rl_env env.py:641-696, run_colav env.py:1430-1474
+    if (sampling_count < G.max_sampling_frequency) {
+      const double a = actions[env];
+      sampling_count += 1;
+      // get_intermediate_waypoints (env.py:198-236)
+      const double l_s = fabs(G.ab_segment_length * tan(a));
+      double e_s = l_s * G.cos_omega;
+      double n_s = l_s * G.sin_omega;
+      if (a > 0) e_s *= -1; else n_s *= -1;
+      const double rn = n_base + n_s, re = e_base + e_s;
+      n_base = rn + G.ab_north_segment_length;
+      e_base = re + G.ab_east_segment_length;
+      if (role == 1) {
+        // update_route: insert before the last waypoint (controllers.py:417-422)
+        dv.buf.iw_f64[(long long)(sampling_count - 1) * B + env] = rn;
+        dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + sampling_count - 1) * B + env] = re;
+        n_iw = sampling_count;
+        s.n_wp = P.n_wp + n_iw;
+      }
+      travel_dist = 0.0; travel_time = 0.0;
+      have_iw = true;
+      // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
+      const bool fail = map_contains(mp, rn, re) ||
+                        ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
+      if (fail) {
+        if (IS_RL) out_reward = (acc_reward >= 0) ? (-acc_reward * 2.0) : (acc_reward * 2.0);
+        snapshot_info = (snapshot_info & 0x7ff) | SHIPENV_EV_SAMPLING_FAILURE | SHIPENV_INFO_TERMINAL;
+        out_info = snapshot_info | SHIPENV_INFO_DONE;
+        flags |= SHIPENV_FLAG_DONE;
+        write_snapshot_only = true;      // obs row (the snapshot) is returned unchanged
+        finished = true;
+      } else if (IS_RL) {
+        acc_reward = 0.0;
+      }
+    }
+  }
+  if (valid) refresh_segment(rt, n_iw, s);
+
+  // ---------------- simulator loop
+  while (__any_sync(FULL_MASK, !finished)) {
+    bool stepped = false, st_done = false, st_terminal = false, st_roa = false;
+    double u_pre = 0.0;
+    if (!finished) {
+      stepped = true;
+      const double dt = P.dt;
+      if (has_stop_branch && s.stop) {
+        // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
+        s.time = s.time + dt;
+        s.time = s.time + dt;
+        o0 = (float)s.north; o1 = (float)s.east; o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct;
+      } else {
+        u_pre = s.u;
+        bool hit = false;
+        if (collav_lane) {
+          // is_collision_imminent on the float32 self.states (check_condition.py:130-140)
+          const float dn = ps_tn - ps_on, de = ps_te - ps_oe;
+          hit = (dn * dn + de * de) < 9000000.0f;
+        }
+        const double pre_n = s.north, pre_e = s.east;
+        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias);
+        o0 = (float)s.north; o1 = (float)s.east;
+        if (role == 1 && IS_IW) {
+          o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct;
+          if (flags & SHIPENV_FLAG_TRACKER) {
+            // travel tracker on the two last logged rows (env.py:526-534)
+            const double tn = pre_n - log_n, te = pre_e - log_e;
+            travel_dist += sqrt(tn * tn + te * te);
+            travel_time += dt;
+          }
+        } else {
+          o2 = (float)s.e_ct;
+        }
+        log_n = pre_n; log_e = pre_e;
+      }
+    }
+    // ---- exchange with the other ship of the pair (all lanes participate)
+    const double p_north = shfl_xor_f64(s.north, 1);
+    const double p_east = shfl_xor_f64(s.east, 1);
+    const double p_yaw = shfl_xor_f64(s.yaw, 1);
+    const double p_time = shfl_xor_f64(s.time, 1);
+    // own partial flags / rewards
+    int my_flags = 0;
+    double ra = 0.0, rb = 0.0;
+    if (stepped) {
+      const double len = P.l_ship;
+      const bool grounding = pos_inside_obstacles(mp, s.north, s.east, len);
+      const double margin = len / 2;
+      const bool outside = (s.north < G.map_min_n + margin || s.north > G.map_max_n - margin) ||
+                           (s.east < G.map_min_e + margin || s.east > G.map_max_e - margin);
+      const double dn = s.north - route_end_n, de = s.east - route_end_e;
+      const bool reached = sqrt(dn * dn + de * de) <= 200.0;
+      bool nav_fail = fabs(s.e_ct) > P.nav_fail_tol;
+      if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
+      my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
+      if (IS_RL) {
+        const double gd = map_distance(mp, s.north, s.east, 1000.0);
+        const double aect = fabs(s.e_ct);
+        if (role == 0) {
+          // test_ship_grounding_reward / test_ship_nav_failure_reward (reward_function.py:359-425)
+          if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : exp(-(gd * gd) / 175000.0);
+          rb = (aect < 3000.0) ? exp(-((aect - 3000.0) * (aect - 3000.0)) / 1250000.0) : 1.0;
+        } else {
+          // obs_ship_grounding_reward / obs_ship_nav_failure_reward (reward_function.py:427-494)
+          if (gd <= 1000.0) ra = -((gd < 0.0) ? 1.0 : exp(-(gd * gd) / 50000.0));
+          rb = -((aect < 500.0) ? exp(-((aect - 500.0) * (aect - 500.0)) / 12500.0) : 1.0);
+        }
+      }
+    }
+    const int p_flags = __shfl_xor_sync(FULL_MASK, my_flags, 1);
+    double p_ra = 0.0, p_rb = 0.0;
+    if (IS_RL) { p_ra = shfl_xor_f64(ra, 1); p_rb = shfl_xor_f64(rb, 1); }
+
+    if (stepped) {
+      nsub += 1;
+      const double t_n = role == 0 ? s.north : p_north, t_e = role == 0 ? s.east : p_east;
+      const double t_yaw = role == 0 ? s.yaw : p_yaw, t_time = role == 0 ? s.time : p_time;
+      const double o_n = role == 1 ? s.north : p_north, o_e = role == 1 ? s.east : p_east;
+      const int t_flags = role == 0 ? my_flags : p_flags, o_flags = role == 1 ? my_flags : p_flags;
+      if (G.collav == SHIPENV_COLLAV_SIMPLE) {   // self.states = next_states (float32)
+        ps_tn = (float)t_n; ps_te = (float)t_e; ps_on = (float)o_n; ps_oe = (float)o_e;
+      }
+      // ship-ship terms (compute_distance.py:16-40, check_condition.py:142-158)
+      const double dx = o_n - t_n, dy = o_e - t_e;
+      const double d2 = dx * dx + dy * dy;
+      const bool is_collision = d2 < 2500.0;
+      const bool t_ground = t_flags & 1, t_nav = t_flags & 2, o_ground = o_flags & 1, o_nav = o_flags & 2;
+      double r_total = 0.0;
+      if (IS_RL) {
+        const double distance = sqrt(d2);
+        double r1 = 0.0;
+        if (distance < 10000.0) {
+          const double phi = atan2(dy, dx);
+          double beta = phi - t_yaw;
+          beta = py_mod(beta + kPi, 2 * kPi) - kPi;
+          const bool overtaking = !(fabs(beta) < 15.0 * (kPi / 180.0)) && (fabs(beta) > 165.0 * (kPi / 180.0));
+          // head-on or crossing -> RewardDesign4(target 0, 2e8); the "overtake" branch is dead code
+          if (!overtaking) r1 = (distance < 0.0) ? 1.0 : exp(-(distance * distance) / 200000000.0);
+        }
+        const double t_ra = role == 0 ? ra : p_ra, t_rb = role == 0 ? rb : p_rb;
+        const double o_ra = role == 1 ? ra : p_ra, o_rb = role == 1 ? rb : p_rb;
+        r_total = ((((r1 + t_ra) + t_rb) + o_ra) + o_rb) / 5;
+        // get_reward_due_to_ships_termination (reward_function.py:272-314)
+        if (is_collision || t_ground || t_nav || o_ground || o_nav) {
+          const double reward = r_total + acc_reward;
+          r_total = 0;
+          if (acc_reward > 0) {
+            if (is_collision) r_total += reward * 10.0;
+            if (t_ground) r_total += reward * 5.0;
+            if (t_nav) r_total += reward * 5.0;
+            if (o_ground) r_total += reward * -2.5;
+            if (o_nav) r_total += reward * -2.5;
+          } else if (acc_reward < 0) {
+            if (is_collision) r_total += reward * -10.0;
+            if (t_ground) r_total += reward * -5.0;
+            if (t_nav) r_total += reward * -5.0;
+            if (o_ground) r_total += reward * 2.5;
+            if (o_nav) r_total += reward * 2.5;
+          }
+        }
+      }
+      // events and env_info (reward_function.py:204-268)
+      int ev = 0;
+      bool terminal = false, ts = false, os = false;
+      if (is_collision) { ev |= SHIPENV_EV_COLLISION; terminal = ts = os = true; }
+      if (t_ground) { ev |= SHIPENV_EV_TEST_GROUNDING; terminal = ts = true; }
+      if (t_nav) { ev |= SHIPENV_EV_TEST_NAV_FAILURE; terminal = ts = true; }
+      if (o_ground) { ev |= SHIPENV_EV_OBS_GROUNDING; terminal = os = true; }
+      if (o_nav) { ev |= SHIPENV_EV_OBS_NAV_FAILURE; terminal = os = true; }
+      if (t_flags & 4) { ev |= SHIPENV_EV_TEST_REACHED; ts = true; }
+      if (t_flags & 8) { ev |= SHIPENV_EV_TEST_OUTSIDE; ts = true; }
+      if (o_flags & 4) { ev |= SHIPENV_EV_OBS_REACHED; os = true; }
+      if (o_flags & 8) { ev |= SHIPENV_EV_OBS_OUTSIDE; os = true; }
+      if (t_time > G.ship[0].sim_time) { ev |= SHIPENV_EV_TIME_LIMIT; ts = os = true; }
+      st_terminal = terminal;
+      if (IS_RL) {                                              // rl_env env.py:603-610
+        st_done = ts && !terminal;
+        if (role == 1 && os && !terminal) s.stop = 1;
+      } else {                                                  // run_colav env.py:1385-1399
+        if (role == 0 && ts && !terminal) s.stop = 1;
+        if (role == 1 && os && !terminal) s.stop = 1;
+        // done needs both stop flags: resolved after the shuffle below
+      }
+      const int step_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
+                            (os ? SHIPENV_INFO_OBS_STOP : 0);
+      out_info = step_info;
+      if (IS_RL) {
+        if (MODE == MODE_STEP) acc_reward += r_total;
+        out_reward = r_total;
+      }
+    }
+    const int p_stop = __shfl_xor_sync(FULL_MASK, s.stop, 1);
+    if (stepped) {
+      if (!IS_RL) st_done = s.stop && p_stop;
+      const bool combined_done = st_terminal || st_done;
+      if (combined_done) out_info |= SHIPENV_INFO_DONE;
+      if (MODE == MODE_SUBSTEPS) {
+        have_obs = true;
+        k_left -= 1;
+        if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
+        else if (k_left <= 0) finished = true;
+      } else {
+        // step() control flow: rl_env env.py:700-771, run_colav env.py:1478-1533
+        if (stage == 0) {
+          // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
+          // (meaningful on the obstacle lane; the test lane receives it below)
+          const double dn = s.north - s.wn, de = s.east - s.we;
+          st_roa = (dn * dn + de * de) < G.roa * G.roa;
+          if (combined_done) { have_obs = true; flags |= SHIPENV_FLAG_DONE; finished = true; }
+        } else if (stage == 1) {
+          have_obs = true;
+          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
+          else if (sampling_count == G.max_sampling_frequency) { travel_dist = 0.0; travel_time = 0.0; stage = 2; }
+          else finished = true;
+        } else {
+          have_obs = true;
+          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
+        }
+      }
+    }
+    if (MODE == MODE_STEP) {
+      // RoA flag lives on the obstacle lane (role 1): broadcast it to the pair
+      const int is_roa = __shfl_sync(FULL_MASK, (int)st_roa, (threadIdx.x & 31) | 1);
+      if (stepped && !finished && stage == 0) {
+        if (is_roa) {
+          if (have_iw) stage = 1;
+          else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finished = true; }
+        }
+      }
+    }
+  }
+
+  // ---------------- epilogue: observation row, outputs, state write-back
+  const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
+  const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
+  const float t2 = __shfl_xor_sync(FULL_MASK, o2, 1);
+  // metric counters: one atomic per warp (all lanes take part in the reduction)
+  const bool touched = valid && (nsub > 0 || write_snapshot_only);
+  {
+    const int sub = __reduce_add_sync(FULL_MASK, (valid && role == 1) ? nsub : 0);
+    const int fin = __reduce_add_sync(FULL_MASK, (touched && role == 1 && (flags & SHIPENV_FLAG_DONE)) ? 1 : 0);
+    if ((threadIdx.x & 31) == 0 && dv.buf.counters) {
+      if (sub) atomicAdd(&dv.buf.counters[0], (unsigned long long)sub);
+      if (fin) atomicAdd(&dv.buf.counters[1], (unsigned long long)fin);
+    }
+  }
+  if (!valid) return;
+  if (!touched) {
+    // environment was already done before this call (or k = 0): state and outputs stay as they are
+    if (role == 1) dv.buf.nsub_i32[env] = 0;
+    return;
+  }
+  store_ship(dv, n_ships, sidx, s);
+  if (role == 1) {
+    if (have_obs) {
+      float4* orow = reinterpret_cast<float4*>(dv.buf.obs_f32 + env * 8);
+      orow[0] = make_float4(t0, t1, t2, o0);
+      orow[1] = IS_IW ? make_float4(o1, o2, o3, o4) : make_float4(o1, o2, 0.f, 0.f);
+      snapshot_info = out_info & ~SHIPENV_INFO_DONE;
+    }
+    double* ef = dv.buf.env_f64;
+    ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
+    ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
+    ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
+    ef[SHIPENV_EF_N_BASE * B + env] = n_base;
+    ef[SHIPENV_EF_E_BASE * B + env] = e_base;
+    ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
+    ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
+    int* ei = dv.buf.env_i32;
+    ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
+    ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot_info;
+    ei[SHIPENV_EI_FLAGS * B + env] = flags;
+    if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+      dv.buf.prev_f32[0 * B + env] = ps_tn; dv.buf.prev_f32[1 * B + env] = ps_te;
+      dv.buf.prev_f32[2 * B + env] = ps_on; dv.buf.prev_f32[3 * B + env] = ps_oe;
+    }
+    if (IS_RL && MODE == MODE_STEP && !write_snapshot_only) out_reward = acc_reward;
+    dv.buf.reward[env] = out_reward;
+    dv.buf.info_i32[env] = out_info;
+    dv.buf.nsub_i32[env] = nsub;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bare ship loop (no env logic): every lane integrates its own ship k steps
+// ------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128)
+k_ship_rollout(DevView dv, int k_steps) {
+  __shared__ SharedBlock sb;
+  stage_params(sb, dv.params);
+  const long long n_ships = 2 * dv.num_envs;
+  const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= n_ships) return;
+  const int role = (int)(sidx & 1);
+  const ShipEnvShipParams& P = sb.p.ship[role];
+  const Route rt{P.wp_north, P.wp_east, nullptr, nullptr, dv.num_envs, P.n_wp};
+  Ship s;
+  load_ship(dv, n_ships, sidx, s);
+  s.n_wp = P.n_wp;
+  refresh_segment(rt, 0, s);
+  for (int i = 0; i < k_steps; ++i) ship_step<MODEL>(P, rt, 0, s, false, 0.0);
+  store_ship(dv, n_ships, sidx, s);
+  if (dv.buf.counters) atomicAdd(&dv.buf.counters[2], (unsigned long long)k_steps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// DFMA peak microbenchmark (roofline denominator; compiled with explicit fma so -fmad=false does not
+// split it)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+}
+
+}  // namespace senv

@@ -1,0 +1,128 @@
+"""Machinery configuration holders.  Mirrors */ship_in_transit/sub_systems/ship_engine.py of the
+reference (class and field names: ship_engine.py:17-163, derived attributes :342-370)."""
+from __future__ import annotations
+
+from typing import List, NamedTuple, Union
+
+import numpy as np
+
+
+class MachineryModeParams(NamedTuple):           # ship_engine.py:17-20
+    main_engine_capacity: float
+    electrical_capacity: float
+    shaft_generator_state: str
+
+
+class MachineryMode:                              # ship_engine.py:23-44
+    def __init__(self, params: MachineryModeParams):
+        self.main_engine_capacity = params.main_engine_capacity
+        self.electrical_capacity = params.electrical_capacity
+        self.shaft_generator_state = params.shaft_generator_state
+        self.available_propulsion_power = 0
+        self.available_propulsion_power_main_engine = 0
+        self.available_propulsion_power_electrical = 0
+
+    def update_available_propulsion_power(self, hotel_load):
+        if self.shaft_generator_state == 'MOTOR':      # PTI
+            self.available_propulsion_power = self.main_engine_capacity + self.electrical_capacity - hotel_load
+            self.available_propulsion_power_main_engine = self.main_engine_capacity
+            self.available_propulsion_power_electrical = self.electrical_capacity - hotel_load
+        elif self.shaft_generator_state == 'GEN':      # PTO
+            self.available_propulsion_power = self.main_engine_capacity - hotel_load
+            self.available_propulsion_power_main_engine = self.main_engine_capacity - hotel_load
+            self.available_propulsion_power_electrical = 0
+        else:                                          # MEC
+            self.available_propulsion_power = self.main_engine_capacity
+            self.available_propulsion_power_main_engine = self.main_engine_capacity
+            self.available_propulsion_power_electrical = 0
+
+
+class MachineryModes:                             # ship_engine.py:78-85
+    def __init__(self, list_of_modes: List[MachineryMode]):
+        self.list_of_modes = list_of_modes
+
+
+class FuelConsumptionCoefficients(NamedTuple):    # ship_engine.py:115-118
+    a: float
+    b: float
+    c: float
+
+
+class SpecificFuelConsumptionWartila6L26:         # ship_engine.py:88-99 (fuel logging is off the step path)
+    def __init__(self):
+        self.a, self.b, self.c = 128.9, -168.9, 246.8
+
+    def fuel_consumption_coefficients(self):
+        return FuelConsumptionCoefficients(a=self.a, b=self.b, c=self.c)
+
+
+class SpecificFuelConsumptionBaudouin6M26Dot3:    # ship_engine.py:101-112
+    def __init__(self):
+        self.a, self.b, self.c = 108.7, -289.9, 324.9
+
+    def fuel_consumption_coefficients(self):
+        return FuelConsumptionCoefficients(a=self.a, b=self.b, c=self.c)
+
+
+class MachinerySystemConfiguration(NamedTuple):   # ship_engine.py:121-138
+    hotel_load: float
+    machinery_modes: MachineryModes
+    machinery_operating_mode: int
+    rated_speed_main_engine_rpm: float
+    linear_friction_main_engine: float
+    linear_friction_hybrid_shaft_generator: float
+    gear_ratio_between_main_engine_and_propeller: float
+    gear_ratio_between_hybrid_shaft_generator_and_propeller: float
+    propeller_inertia: float
+    propeller_speed_to_torque_coefficient: float
+    propeller_diameter: float
+    propeller_speed_to_thrust_force_coefficient: float
+    rudder_angle_to_sway_force_coefficient: float
+    rudder_angle_to_yaw_force_coefficient: float
+    max_rudder_angle_degrees: float
+    specific_fuel_consumption_coefficients_me: FuelConsumptionCoefficients
+    specific_fuel_consumption_coefficients_dg: FuelConsumptionCoefficients
+
+
+class RudderConfiguration(NamedTuple):            # ship_engine.py:160-163
+    rudder_angle_to_sway_force_coefficient: float
+    rudder_angle_to_yaw_force_coefficient: float
+    max_rudder_angle_degrees: float
+
+
+class _Integrator:
+    """Holder for the integrator step (EulerInt, utils/utils.py:7-53); integration happens on the GPU."""
+
+    def __init__(self, dt=0.01, sim_time=10):
+        self.dt = dt
+        self.sim_time = sim_time
+        self.time = 0.0
+
+
+class ShipMachineryModel:
+    """Parameter holder with the attribute names of ShipMachineryModel (ship_engine.py:341-401)."""
+
+    def __init__(self, machinery_config: MachinerySystemConfiguration,
+                 initial_propeller_shaft_speed_rad_per_sec: float, time_step: float):
+        self.machinery_modes = machinery_config.machinery_modes
+        self.hotel_load = machinery_config.hotel_load
+        for mode in self.machinery_modes.list_of_modes:            # ship_engine.py:229-234
+            mode.update_available_propulsion_power(self.hotel_load)
+        self.mode = self.machinery_modes.list_of_modes[machinery_config.machinery_operating_mode]
+        self.c_rudder_v = machinery_config.rudder_angle_to_sway_force_coefficient
+        self.c_rudder_r = machinery_config.rudder_angle_to_yaw_force_coefficient
+        self.rudder_ang_max = machinery_config.max_rudder_angle_degrees * np.pi / 180
+        self.w_rated_me = machinery_config.rated_speed_main_engine_rpm * np.pi / 30
+        self.d_me = machinery_config.linear_friction_main_engine
+        self.d_hsg = machinery_config.linear_friction_hybrid_shaft_generator
+        self.r_me = machinery_config.gear_ratio_between_main_engine_and_propeller
+        self.r_hsg = machinery_config.gear_ratio_between_hybrid_shaft_generator_and_propeller
+        self.jp = machinery_config.propeller_inertia
+        self.kp = machinery_config.propeller_speed_to_torque_coefficient
+        self.dp = machinery_config.propeller_diameter
+        self.kt = machinery_config.propeller_speed_to_thrust_force_coefficient
+        self.shaft_speed_max = 1.1 * self.w_rated_me * self.r_me
+        self.omega = initial_propeller_shaft_speed_rad_per_sec
+        self.time_step = time_step
+        self.int = _Integrator(dt=time_step)
+        self._initial_parameters = {'omega': self.omega}

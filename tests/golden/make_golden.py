@@ -12,6 +12,7 @@ geometry results come from the Shapely stand-in of oracle/ref_harness.py (Shapel
 from __future__ import annotations
 
 import ctypes
+import json
 import os
 import sys
 
@@ -94,8 +95,9 @@ def bare_rollout(kind: str, dt, who: int, n_steps: int, mode="PTI", post_reset=F
         wpt[i] = a.auto_pilot.next_wpt
     # keep the first 256 steps, then every 16th, and always the last
     keep = np.unique(np.concatenate([np.arange(min(256, n_steps)), np.arange(15, n_steps, 16), [n_steps - 1]]))
+    meta = dict(kind=kind, dt=dt, who=who, mode=mode, post_reset=post_reset)
     return dict(cfg=struct_bytes(cfg), n_steps=n_steps, step_index=keep + 1, states=states[keep],
-                ctrl=ctrl[keep], next_wpt=wpt, dt_shaft=cfg.dt_shaft)
+                ctrl=ctrl[keep], next_wpt=wpt, dt_shaft=cfg.dt_shaft, meta=json.dumps(meta))
 
 
 def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None, obs_init=None, sim_time=10000):
@@ -110,7 +112,8 @@ def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None
     cfg = O.env_config_from_assets(assets, env.map, args, env_kind)
     obs0 = env.reset()
     n = len(actions)
-    out = dict(cfg=struct_bytes(cfg), actions=np.asarray(actions, dtype=np.float64), obs0=np.asarray(obs0),
+    meta = dict(kind=kind, dt=dt, collav=collav, mode=mode, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
+    out = dict(meta=json.dumps(meta), cfg=struct_bytes(cfg), actions=np.asarray(actions, dtype=np.float64), obs0=np.asarray(obs0),
                obs=np.zeros((n, 8), np.float32), reward=np.zeros(n), done=np.zeros(n, np.int32),
                events=np.zeros(n, np.int32), terminal=np.zeros(n, np.int32), test_stop=np.zeros(n, np.int32),
                obs_stop=np.zeros(n, np.int32), n_log=np.zeros(n, np.int32), k_test=np.zeros(n, np.int32),
@@ -174,7 +177,8 @@ def noniw_run(dt, collav="none", max_steps=4000, test_init=None, obs_init=None, 
         kt.append(assets[0].auto_pilot.next_wpt); ko.append(assets[1].auto_pilot.next_wpt)
         if d:
             break
-    return dict(cfg=struct_bytes(cfg), obs=np.asarray(obs, np.float32), events=np.asarray(ev, np.int32),
+    meta = dict(kind="noniw", dt=dt, collav=collav, test_init=test_init, obs_init=obs_init, use_reset=use_reset)
+    return dict(meta=json.dumps(meta), cfg=struct_bytes(cfg), obs=np.asarray(obs, np.float32), events=np.asarray(ev, np.int32),
                 terminal=np.asarray(term, np.int32), test_stop=np.asarray(ts, np.int32),
                 obs_stop=np.asarray(os_, np.int32), done=np.asarray(done, np.int32),
                 test_state=np.asarray(tst), obs_state=np.asarray(ost), k_test=np.asarray(kt, np.int32),

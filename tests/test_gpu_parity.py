@@ -1,0 +1,387 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every test drives the CUDA kernels through
+the C ABI (include/shipenv.h via ast_sac_b200) and checks them against
+
+  * the golden vectors produced by the unmodified Python reference (tests/golden/*.npz), and
+  * the CPU oracle (oracle/shipsim_oracle.c) on the same seeded inputs,
+
+with flags / event bits / waypoint indices / step counts bit-exact and FP64 states within
+REL_TOL = 1e-9 relative (BASELINE.json north_star), plus size-independent properties at
+BASELINE.json's full sizes (1e5 / 1e6 environments).
+"""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from ast_sac_b200 import _lib as L
+from ast_sac_b200 import scenarios as S
+from oracle import oracle as O
+
+from helpers import (CTRL_SCALE, REL_TOL, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
+                     rel_err, struct_from_bytes)
+from product_helpers import env_from_meta, product_ctrl_vec, product_ship_vec, product_states_all
+
+pytestmark = pytest.mark.gpu
+
+
+def _sync():
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# golden fixtures from the reference: IW episodes (KAT2 / KAT4 and the rare-event cases)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_"))
+def test_iw_episode_matches_reference_golden(name):
+    g = golden(name)
+    meta = json.loads(str(g["meta"]))
+    env, assets = env_from_meta(meta)
+    is_rl = meta["kind"] == "rl"
+    obs0 = env.reset()
+    assert np.array_equal(np.asarray(obs0), g["obs0"])
+    n = int(g["n_valid"])
+    for j in range(n):
+        res = env.step(np.array([g["actions"][j]]))
+        if is_rl:
+            o, r, d, info = res
+        else:
+            o, d, info = res
+            r = 0.0
+        bits = int(env.info_buf[0].item())
+        assert d == bool(g["done"][j]), (name, j)
+        assert (bits & L.INFO_EVENT_MASK) == g["events"][j], (name, j, info["events"])
+        assert info["terminal"] == bool(g["terminal"][j])
+        assert info["test_ship_stop"] == bool(g["test_stop"][j])
+        assert info["obs_ship_stop"] == bool(g["obs_stop"][j])
+        k = env.next_wpt[0].cpu().numpy()
+        assert k[0] == g["k_test"][j] and k[1] == g["k_obs"][j], (name, j, k)
+        for role, key in ((0, "test"), (1, "obs")):
+            e = rel_err(product_ship_vec(env, role), g[key + "_state"][j], STATE_SCALE)
+            assert e.max() < REL_TOL, (name, j, key, e)
+            e = rel_err(product_ctrl_vec(env, role), g[key + "_ctrl"][j], CTRL_SCALE)
+            assert e.max() < REL_TOL, (name, j, key, "ctrl", e)
+        assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < REL_TOL
+        np.testing.assert_allclose(o, g["obs"][j], rtol=2e-7, atol=1e-6)
+        if is_rl:
+            assert rel_err(r, g["reward"][j], 1e-3) < 1e-8, (name, j, r, g["reward"][j])
+    # number of simulator steps: the reference log has one row per _step() plus the init_step row
+    # (a sampling failure adds none)
+    assert env.total_substeps() == int(g["n_log"][n - 1]) - 1
+    rn, re = env.obs_route()
+    assert rel_err(rn, g["obs_route_north"], 1.0).max() < 1e-12
+    assert rel_err(re, g["obs_route_east"], 1.0).max() < 1e-12
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_names("colav_noniw_"))
+def test_noniw_run_matches_reference_golden(name):
+    """config 1 (run_colav/run_simplified_model.py): init_step() + _step() loop, one launch per step."""
+    g = golden(name)
+    meta = json.loads(str(g["meta"]))
+    env, _ = env_from_meta(meta)
+    if meta["use_reset"]:
+        env.reset()
+    else:
+        env.init_step()
+    n = len(g["done"])
+    tol = 1e-6 if meta["dt"] == 30 else REL_TOL   # dt = 30: explicit-Euler amplification, SURVEY.md section 7
+    for i in range(n):
+        o, d, info = env._step()
+        bits = int(env.info_buf[0].item())
+        assert d == bool(g["done"][i]), (name, i)
+        assert (bits & L.INFO_EVENT_MASK) == g["events"][i], (name, i, info["events"])
+        assert info["terminal"] == bool(g["terminal"][i]) and info["test_ship_stop"] == bool(g["test_stop"][i])
+        assert info["obs_ship_stop"] == bool(g["obs_stop"][i])
+        k = env.next_wpt[0].cpu().numpy()
+        assert k[0] == g["k_test"][i] and k[1] == g["k_obs"][i]
+        if i % 16 == 0 or i > n - 40:
+            for role, key in ((0, "test_state"), (1, "obs_state")):
+                v = np.append(product_ship_vec(env, role), env.read_ship_state(role)[L.SF["time"]])
+                e = rel_err(v, g[key][i], np.append(STATE_SCALE, 1.0))
+                assert e.max() < tol, (name, i, key, e)
+        np.testing.assert_allclose(o, g["obs"][i], rtol=2e-7, atol=1e-6)
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_names("bare_"))
+def test_bare_ship_rollout_matches_reference_golden(name):
+    """KAT1 / KAT3: bare ship + controllers loop over 10k (simple) / 4k (detailed) steps."""
+    g = golden(name)
+    meta = json.loads(str(g["meta"]))
+    kind = "colav" if meta["kind"] == "simple" else "rl"
+    env, _ = env_from_meta(dict(kind="noniw" if kind == "colav" else "rl", dt=meta["dt"], mode=meta.get("mode", "PTI")))
+    if meta["post_reset"] and kind == "rl":
+        # reset() leaves the machinery at dt_shaft = 0.01; rebuild the un-stepped initial state after it
+        env.reset()
+        L.check(L.load().shipenv_construct(env._handle, None, env._stream_ptr()))
+    role = meta["who"]
+    steps = g["step_index"]
+    detailed = kind == "rl"
+    cfg = struct_from_bytes(O.ShipConfig, g["cfg"])
+    tol = 1e-7 if meta["dt"] == 30 else REL_TOL
+    if detailed:
+        end_n, end_e = cfg.wp_north[cfg.n_wp - 1], cfg.wp_east[cfg.n_wp - 1]
+        d_end = np.hypot(g["states"][:, 0] - end_n, g["states"][:, 1] - end_e)
+        arrived = np.nonzero(d_end < 300.0)[0]
+        last_row = arrived[0] if len(arrived) else len(d_end) - 1
+    else:
+        last_row = len(steps) - 1
+    done = 0
+    for row in range(last_row + 1):
+        env.ship_rollout(int(steps[row]) - done)
+        done = int(steps[row])
+        if row % 8 == 0 or row == last_row:
+            e = rel_err(product_ship_vec(env, role), g["states"][row], STATE_SCALE)
+            assert e.max() < tol, (name, row, e)
+            assert int(env.next_wpt[0, role]) == g["next_wpt"][done - 1]
+    env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched runs against the CPU oracle on the same seeded inputs
+# ------------------------------------------------------------------------------------------------
+def _oracle_cfg(assets, env, kind):
+    return O.env_config_from_assets(assets, env.map, env.args, kind)
+
+
+@pytest.mark.parametrize("kind,collav", [("rl", "none"), ("colav", "none"), ("rl", "simple"), ("colav", "simple")])
+def test_batched_episodes_match_oracle(kind, collav):
+    """256 environments, per-env random scoping angles and jittered start positions, full episodes
+    (9 step() calls); every environment is compared with its own scalar oracle run."""
+    B = 256
+    args = S.get_env_args(time_step=4, collav_mode=collav)
+    if kind == "rl":
+        assets, m = S.build_rl_assets(args)
+    else:
+        assets, m = S.build_colav_assets(args, iw=True)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=100.0, seed=1)
+    cls_kind = O.ENV_RL if kind == "rl" else O.ENV_COLAV_IW
+    if kind == "rl":
+        env, assets = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+    else:
+        env, assets = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init)
+    gen = torch.Generator().manual_seed(0)
+    actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
+    actions[: B // 4] *= 0.1          # small angles keep the ships on a collision course
+    env.reset()
+    init_np = init.cpu().numpy().reshape(7, B, 2)
+    base_cfg = _oracle_cfg(assets, env, cls_kind)
+    oracles = []
+    for b in range(B):
+        cfg = O.EnvConfig()
+        C.memmove(C.byref(cfg), C.byref(base_cfg), C.sizeof(O.EnvConfig))
+        for role in range(2):
+            cfg.ship[role].initial_north_position_m = init_np[0, b, role]
+            cfg.ship[role].initial_east_position_m = init_np[1, b, role]
+        oe = O.OracleEnv(cfg)
+        oe.reset()
+        oracles.append(oe)
+    alive = np.ones(B, dtype=bool)
+    seen_events = 0
+    for j in range(9):
+        res = env.step(actions[:, j].cuda())
+        _sync()
+        info = env.info_buf.cpu().numpy()
+        nsub = env.nsub_buf.cpu().numpy()
+        obs = env.obs_buf.cpu().numpy()
+        rew = env.reward_buf.cpu().numpy()
+        states = product_states_all(env)
+        kk = env.next_wpt.cpu().numpy()
+        for b in range(B):
+            if not alive[b]:
+                assert nsub[b] == 0          # finished environments are left alone
+                continue
+            r = oracles[b].step(float(actions[b, j]))
+            assert r.error == 0
+            assert nsub[b] == r.n_substeps, (b, j, nsub[b], r.n_substeps)
+            assert (info[b] & L.INFO_EVENT_MASK) == r.events, (b, j)
+            assert bool(info[b] & L.INFO_DONE) == bool(r.done)
+            assert bool(info[b] & L.INFO_TERMINAL) == bool(r.terminal)
+            assert bool(info[b] & L.INFO_TEST_STOP) == bool(r.test_ship_stop)
+            assert bool(info[b] & L.INFO_OBS_STOP) == bool(r.obs_ship_stop)
+            st = oracles[b].st
+            assert kk[b, 0] == st.ship[0].next_wpt and kk[b, 1] == st.ship[1].next_wpt
+            for role in range(2):
+                e = rel_err(states[b, role], oracle_ship_vec(st.ship[role]), STATE_SCALE)
+                assert e.max() < REL_TOL, (b, j, role, e)
+            np.testing.assert_allclose(obs[b], np.array(r.obs[:]), rtol=2e-7, atol=1e-6)
+            if kind == "rl":
+                assert rel_err(rew[b], r.reward, 1e-3) < 1e-8, (b, j, rew[b], r.reward)
+            seen_events |= r.events
+            if r.done:
+                alive[b] = False
+    assert not alive.any()
+    # the batch must have exercised several different endings
+    assert bin(seen_events).count("1") >= 5, bin(seen_events)
+    env.close()
+
+
+def test_substeps_split_invariance_and_masked_reset():
+    """k x _step() in one launch == the same k steps in several launches (state stays in registers
+    vs round-trips through HBM), bit for bit; masked reset only touches the selected environments."""
+    B = 4096
+    args = S.get_env_args(time_step=4)
+    assets, _ = S.build_rl_assets(args)
+    init = S.jittered_init_states(assets, B, seed=3)
+    env_a, _ = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+    env_b, _ = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+    env_a.reset(); env_b.reset()
+    env_a._step(96)
+    for k in (1, 7, 24, 64):
+        env_b._step(k)
+    _sync()
+    assert torch.equal(env_a.ship_f64, env_b.ship_f64)
+    assert torch.equal(env_a.ship_i32, env_b.ship_i32)
+    assert torch.equal(env_a.env_f64, env_b.env_f64)
+    assert torch.equal(env_a.obs_buf, env_b.obs_buf)
+    assert env_a.total_substeps() == env_b.total_substeps() == 96 * B
+    # masked reset
+    before = env_a.ship_f64.clone()
+    mask = torch.zeros(B, dtype=torch.bool, device="cuda")
+    mask[::3] = True
+    env_a.reset(mask=mask)
+    _sync()
+    s = env_a.ship_f64.view(L.SF_COUNT, B, 2)
+    b4 = before.view(L.SF_COUNT, B, 2)
+    assert torch.equal(s[:, ~mask], b4[:, ~mask])
+    assert torch.all(s[L.SF["time"], mask] == 4.0)
+    env_a.close(); env_b.close()
+
+
+def test_full_size_properties_1e5_envs():
+    """BASELINE config 2 size (1e5 SimpleShipModel pairs): identical environments stay identical, the
+    device counters equal the per-env step counts, and every environment terminates."""
+    B = 100_000
+    args = S.get_env_args(time_step=4)
+    env, assets = S.prepare_colav_env(args, iw=True, num_envs=B)
+    env.reset()
+    gen = torch.Generator().manual_seed(0)
+    a64 = (torch.rand((64, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
+    actions = a64.repeat((B + 63) // 64, 1)[:B].cuda()      # env b uses action row b % 64
+    total = 0
+    for j in range(9):
+        env.step(actions[:, j])
+        total += int(env.nsub_buf.sum().item())
+    _sync()
+    assert env.total_substeps() == total
+    assert bool(env.done_mask.all())
+    st = env.ship_f64.view(L.SF_COUNT, B, 2)
+    # environments 64 apart received identical inputs -> bit-identical trajectories
+    assert torch.equal(st[:, :64], st[:, 64:128])
+    ref = st[:, :64].repeat(1, (B + 63) // 64, 1)[:, :B]
+    assert torch.equal(st, ref)
+    # and the first 64 match the scalar oracle
+    cfg = O.env_config_from_assets(assets, env.map, env.args, O.ENV_COLAV_IW)
+    states = product_states_all(env)
+    for b in range(0, 64, 7):
+        oe = O.OracleEnv(cfg)
+        oe.reset()
+        for j in range(9):
+            r = oe.step(float(a64[b, j]))
+            if r.done:
+                break
+        for role in range(2):
+            e = rel_err(states[b, role], oracle_ship_vec(oe.st.ship[role]), STATE_SCALE)
+            assert e.max() < REL_TOL, (b, role, e)
+        assert (int(env.info_buf[b]) & L.INFO_EVENT_MASK) == r.events
+    env.close()
+
+
+def test_full_size_bare_rollout_1e6_ships_10k_steps_sample():
+    """BASELINE config 3 size: 1e6 detailed-model pairs integrate the bare loop; every ship of a role is
+    bit-identical (same inputs), and the result matches the oracle after 1000 steps."""
+    B = 1_000_000
+    args = S.get_env_args(time_step=4)
+    env, assets = S.prepare_multiship_rl_env(args, num_envs=B)
+    env.ship_rollout(1000)
+    _sync()
+    st = env.ship_f64.view(L.SF_COUNT, B, 2)
+    assert torch.equal(st[:, 1:], st[:, :1].expand(-1, B - 1, -1))
+    for role in range(2):
+        cfg = O.ship_config_from_asset(assets[role])
+        out, wpt, _ = O.ship_rollout(cfg, 1000)
+        e = rel_err(product_ship_vec(env, role, e=B - 1), out[-1], STATE_SCALE)
+        assert e.max() < REL_TOL, (role, e)
+        assert int(env.next_wpt[B - 1, role]) == wpt[-1]
+    env.close()
+
+
+def test_host_buffer_entry_points_match_device_path():
+    """shipenv_reset_host / shipenv_step_host (numpy in, numpy out through the C ABI)."""
+    B = 512
+    args = S.get_env_args(time_step=4)
+    env_d, _ = S.prepare_multiship_rl_env(args, num_envs=B)
+    env_h, _ = S.prepare_multiship_rl_env(args, num_envs=B)
+    gen = np.random.default_rng(5)
+    actions = gen.uniform(-np.pi / 6, np.pi / 6, size=(B, 3))
+    env_d.reset()
+    obs0 = env_h.reset_host()
+    assert np.array_equal(obs0, env_d.obs_buf.cpu().numpy())
+    for j in range(3):
+        env_d.step(torch.from_numpy(actions[:, j]).cuda())
+        obs, rew, info, nsub = env_h.step_host(actions[:, j])
+        _sync()
+        assert np.array_equal(obs, env_d.obs_buf.cpu().numpy())
+        assert np.array_equal(rew, env_d.reward_buf.cpu().numpy())
+        assert np.array_equal(info, env_d.info_buf.cpu().numpy())
+        assert np.array_equal(nsub, env_d.nsub_buf.cpu().numpy())
+    env_d.close(); env_h.close()
+
+
+def test_c_abi_standalone_without_torch_buffers():
+    """The library used as a plain C library: shipenv_alloc owns the device memory."""
+    from ast_sac_b200 import env as E
+    lib = L.load()
+    args = S.get_env_args(time_step=4)
+    assets, m = S.build_colav_assets(args, iw=True)
+    P = E.pack_params(assets, m, args, L.ENV_COLAV_IW, post_reset=True)
+    h = C.c_void_p()
+    B = 1000
+    L.check(lib.shipenv_create(C.byref(P), B, 0, C.byref(h)))
+    assert lib.shipenv_step_host(h, None, None, None, None, None) != 0      # no buffers yet -> error code
+    assert b"shipenv_bind" in lib.shipenv_last_error()
+    L.check(lib.shipenv_alloc(h))
+    obs = np.zeros((B, 8), np.float32)
+    L.check(lib.shipenv_reset_host(h, None, obs.ctypes.data))
+    assert np.allclose(obs[0], [100, 100, 0, 9900, 14900, -135 * np.pi / 180, 0, 3.5])
+    actions = np.full(B, np.deg2rad(-2.0))
+    rew = np.zeros(B); info = np.zeros(B, np.int32); nsub = np.zeros(B, np.int32)
+    L.check(lib.shipenv_step_host(h, actions.ctypes.data, obs.ctypes.data, rew.ctypes.data, info.ctypes.data,
+                                  nsub.ctypes.data))
+    assert (nsub == 76).all()            # KAT2: 77 log rows after the first step() = init_step + 76 _step()
+    cnt = (C.c_ulonglong * 4)()
+    L.check(lib.shipenv_read_counters(h, cnt))
+    assert cnt[0] == 76 * B
+    L.check(lib.shipenv_destroy(h))
+
+
+def test_step_after_budget_raises_like_reference():
+    """Quirk 7: step() with the sampling budget exhausted and the obstacle ship
+    inside a radius of acceptance leaves next_observations unbound in the reference."""
+    args = S.get_env_args(time_step=4, max_sampling_frequency=1)
+    env, _ = S.prepare_colav_env(args, iw=True)
+    env.reset()
+    o, d, info = env.step(np.array([0.0]))      # last sampling: runs to completion
+    assert d
+    env2, _ = S.prepare_colav_env(S.get_env_args(time_step=4, max_sampling_frequency=0), iw=True)
+    env2.reset()
+    # no sampling allowed: the loop runs until the obstacle ship reaches the RoA of the route end
+    with pytest.raises(UnboundLocalError):
+        env2.step(np.array([0.0]))
+    env.close(); env2.close()
+
+
+def test_pickle_roundtrip_rebuilds_device_state():
+    import pickle
+    args = S.get_env_args(time_step=4)
+    env, _ = S.prepare_multiship_rl_env(args)
+    env.reset()
+    env2 = pickle.loads(pickle.dumps(env))
+    o = env2.reset()
+    assert np.array_equal(o, env.initial_states)
+    r1 = env.step(np.array([0.01]))
+    r2 = env2.step(np.array([0.01]))
+    assert np.array_equal(r1[0], r2[0]) and r1[1] == r2[1]
+    env.close(); env2.close()
