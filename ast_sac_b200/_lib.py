@@ -9,10 +9,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libshipenv.so")
+# AST_SAC_B200_LIB overrides the library path (used to compare build variants, e.g. SENV_MIN_BLOCKS)
+LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 1
+ABI_VERSION = 2
+MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED = 0, 1
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
 COLLAV_NONE, COLLAV_SIMPLE = 0, 1
@@ -31,12 +33,12 @@ EI_COUNT = 3
 _D = C.c_double
 SHIP_PARAM_DOUBLES = [
     "mass", "i_z", "x_du", "y_dv", "n_dr", "lin_damp_u", "lin_damp_v", "lin_damp_r", "ku", "kv", "kr",
-    "inv_m_u", "inv_m_v", "inv_m_r", "cur_n", "cur_e", "wind_speed", "wind_dir",
+    "inv_m_u", "inv_m_v", "inv_m_r", "cur_n", "cur_e", "wind_speed", "wind_dir", "cos_wind_dir", "sin_wind_dir",
     "proj_area_f", "proj_area_l", "l_ship", "c_rudder_v", "c_rudder_r",
     "init_north", "init_east", "init_yaw", "init_u", "init_v", "init_r", "init_omega",
     "dt", "sim_time", "dt_shaft", "spd_kp", "spd_kd", "spd_ki", "max_thrust",
     "kp_ship_speed", "ki_ship_speed", "kp_shaft_speed", "ki_shaft_speed", "max_shaft_speed", "init_shaft_err_i",
-    "ctrl_dt", "hdg_kp", "hdg_kd", "hdg_ki", "max_rudder", "los_ra", "los_r", "los_ki", "los_limit",
+    "ctrl_dt", "inv_ctrl_dt", "hdg_kp", "hdg_kd", "hdg_ki", "max_rudder", "los_ra", "los_r", "los_ki", "los_limit",
     "desired_speed", "p_me", "p_el", "tq_me_max", "tq_el_max", "d_me", "d_hsg", "r_me", "r_hsg", "jp",
     "k_torque", "thrust_coeff", "nav_fail_tol",
 ]
@@ -55,7 +57,7 @@ class Params(C.Structure):
                 ("cos_omega", _D), ("sin_omega", _D), ("n_base0", _D), ("e_base0", _D), ("roa", _D),
                 ("poly_start", C.c_int32 * (MAX_POLY + 1)), ("n_poly", C.c_int32), ("env_kind", C.c_int32),
                 ("collav", C.c_int32), ("max_sampling_frequency", C.c_int32), ("abi_version", C.c_int32),
-                ("pad_", C.c_int32)]
+                ("math_mode", C.c_int32)]
 
 
 class Buffers(C.Structure):

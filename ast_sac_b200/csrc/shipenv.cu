@@ -8,10 +8,11 @@
 #include <cstring>
 #include <new>
 
-#include "shipenv.h"
-#include "shipenv_kernels.cuh"
+#include <cmath>
+#include <vector>
 
-using senv::DevView;
+#include "shipenv.h"
+#include "shipenv_launch.h"
 
 namespace {
 
@@ -31,8 +32,6 @@ int fail(int code, const char* fmt, ...) {
     if (e__ != cudaSuccess) return fail(SHIPENV_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
   } while (0)
 
-constexpr int kBlock = 128;
-
 }  // namespace
 
 struct shipenv {
@@ -44,6 +43,9 @@ struct shipenv {
   bool bound = false;
   bool owns = false;
   bool constructed = false;
+  const double* init_dev = nullptr;   // per-ship initial states given to shipenv_construct (caller-owned)
+  unsigned* grid_dev = nullptr;       // culling grid cells
+  SenvGrid grid{};
   // staging for the *_host entry points
   double* act_dev = nullptr;
   uint8_t* mask_dev = nullptr;
@@ -65,6 +67,8 @@ int validate(const ShipEnvParams* p, long long num_envs) {
   if (p->max_sampling_frequency < 0 || p->max_sampling_frequency > SHIPENV_MAX_IW)
     return fail(SHIPENV_E_ARG, "max_sampling_frequency must be in [0, %d]", SHIPENV_MAX_IW);
   if (p->n_poly < 0 || p->n_poly > SHIPENV_MAX_POLY) return fail(SHIPENV_E_ARG, "n_poly out of range");
+  if (p->math_mode != SHIPENV_MATH_STRICT && p->math_mode != SHIPENV_MATH_FAST)
+    return fail(SHIPENV_E_ARG, "math_mode must be SHIPENV_MATH_STRICT or SHIPENV_MATH_FAST");
   if (p->n_poly > 0 && (p->poly_start[0] != 0 || p->poly_start[p->n_poly] > SHIPENV_MAX_VERT))
     return fail(SHIPENV_E_ARG, "polygon vertex table out of range");
   for (int i = 0; i < p->n_poly; ++i)
@@ -85,9 +89,7 @@ int validate(const ShipEnvParams* p, long long num_envs) {
   return SHIPENV_OK;
 }
 
-DevView view(const shipenv* h) { return DevView{h->params_dev, h->buf, h->num_envs}; }
-
-int ship_grid(const shipenv* h) { return (int)((2 * h->num_envs + kBlock - 1) / kBlock); }
+SenvView view(const shipenv* h) { return SenvView{h->params_dev, h->buf, h->num_envs, h->grid}; }
 
 int check_ready(const shipenv* h, bool need_constructed) {
   if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
@@ -97,29 +99,98 @@ int check_ready(const shipenv* h, bool need_constructed) {
   return SHIPENV_OK;
 }
 
-template <int MODEL>
 int launch_reset(shipenv* h, const uint8_t* mask, const double* init, int do_init, int reinit, cudaStream_t st) {
-  senv::k_reset<MODEL><<<ship_grid(h), kBlock, 0, st>>>(view(h), mask, init, do_init, reinit);
-  CUDA_TRY(cudaGetLastError());
+  const int model = h->params.ship[0].model_kind;
+  cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
+                      ? senv_fast::launch_reset(view(h), model, mask, init, do_init, reinit, st)
+                      : senv_strict::launch_reset(view(h), model, mask, init, do_init, reinit, st);
+  if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "reset kernel launch: %s", cudaGetErrorString(e));
   return SHIPENV_OK;
 }
 
-template <int MODEL, int MODE>
-int launch_env(shipenv* h, const double* actions, int k, cudaStream_t st) {
-  const int grid = ship_grid(h);
-  switch (h->params.env_kind) {
-    case SHIPENV_ENV_COLAV_NONIW:
-      senv::k_env<MODEL, SHIPENV_ENV_COLAV_NONIW, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
-      break;
-    case SHIPENV_ENV_COLAV_IW:
-      senv::k_env<MODEL, SHIPENV_ENV_COLAV_IW, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
-      break;
-    default:
-      senv::k_env<MODEL, SHIPENV_ENV_RL, MODE><<<grid, kBlock, 0, st>>>(view(h), actions, k);
-      break;
-  }
-  CUDA_TRY(cudaGetLastError());
+int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t st) {
+  const int model = h->params.ship[0].model_kind;
+  cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
+                      ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, st)
+                      : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, st);
+  if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
   return SHIPENV_OK;
+}
+
+// ---- culling grid ------------------------------------------------------------------------------
+bool host_poly_contains(const ShipEnvParams& p, int poly, double x, double y) {
+  const int a = p.poly_start[poly], b = p.poly_start[poly + 1];
+  bool inside = false;
+  for (int i = a, j = b - 1; i < b; j = i++) {
+    const double xi = p.vert_e[i], yi = p.vert_n[i], xj = p.vert_e[j], yj = p.vert_n[j];
+    if ((yi > y) != (yj > y)) {
+      if (x < (xj - xi) * (y - yi) / (yj - yi) + xi) inside = !inside;
+    }
+  }
+  return inside;
+}
+
+double host_ring_distance(const ShipEnvParams& p, int poly, double x, double y) {
+  const int a = p.poly_start[poly], b = p.poly_start[poly + 1];
+  double best = INFINITY;
+  for (int i = a; i < b; ++i) {
+    const int k = (i + 1 < b) ? i + 1 : a;
+    const double ax = p.vert_e[i], ay = p.vert_n[i], dx = p.vert_e[k] - ax, dy = p.vert_n[k] - ay;
+    const double l2 = dx * dx + dy * dy;
+    double t = l2 > 0 ? ((x - ax) * dx + (y - ay) * dy) / l2 : 0.0;
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    best = std::fmin(best, std::hypot(x - (ax + t * dx), y - (ay + t * dy)));
+  }
+  return best;
+}
+
+// A polygon can only contain a corner of the ship square (centre in the cell, corners at most
+// margin*sqrt(2) from the centre) if the cell centre is inside it or its ring is within
+// halfdiag + margin*sqrt(2) of the cell centre (the ring distance is 1-Lipschitz); likewise a ring
+// can only be within `clip` of a point of the cell if it is within clip + halfdiag of the centre.
+int build_grid(shipenv* h) {
+  const ShipEnvParams& p = h->params;
+  const double w = p.map_max_e - p.map_min_e, ht = p.map_max_n - p.map_min_n;
+  int nx = 1, ny = 1;
+  double cell = 1.0;
+  if (p.n_poly > 0 && w > 0 && ht > 0) {
+    cell = std::fmax(std::fmax(w, ht) / 256.0, 50.0);
+    nx = (int)std::ceil(w / cell);
+    ny = (int)std::ceil(ht / cell);
+  }
+  std::vector<unsigned> cells((size_t)nx * ny, 0u);
+  const double half_len = 0.5 * std::fmax(p.ship[0].l_ship, p.ship[1].l_ship);
+  const double halfdiag = cell * 0.70710678118654757 + 1e-6 * cell;
+  const double r_contains = halfdiag + half_len * 1.4142135623730951 + 1.0;
+  const double r_dist = 1000.0 + halfdiag + 1.0;
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+      const double cx = p.map_min_e + (ix + 0.5) * cell, cy = p.map_min_n + (iy + 0.5) * cell;
+      unsigned m = 0;
+      for (int q = 0; q < p.n_poly && q < 16; ++q) {
+        const double d = host_ring_distance(p, q, cx, cy);
+        if (d <= r_contains || host_poly_contains(p, q, cx, cy)) m |= 1u << q;
+        if (d <= r_dist) m |= 1u << (16 + q);
+      }
+      cells[(size_t)iy * nx + ix] = m;
+    }
+  if (h->grid_dev) cudaFree(h->grid_dev);
+  CUDA_TRY(cudaMalloc(&h->grid_dev, cells.size() * sizeof(unsigned)));
+  CUDA_TRY(cudaMemcpy(h->grid_dev, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  h->grid = SenvGrid{h->grid_dev, p.map_min_e, p.map_min_n, 1.0 / cell, nx, ny};
+  return SHIPENV_OK;
+}
+
+// DFMA peak microbenchmark (roofline denominator)
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
 }
 
 int ensure_staging(shipenv* h) {
@@ -197,6 +268,12 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
     delete h;
     return fail(SHIPENV_E_CUDA, "uploading parameters: %s", cudaGetErrorString(ce));
   }
+  rc = build_grid(h);
+  if (rc) {
+    cudaFree(h->params_dev);
+    delete h;
+    return rc;
+  }
   *out = h;
   return SHIPENV_OK;
 }
@@ -210,6 +287,7 @@ int shipenv_destroy(shipenv_t* h) {
     cudaFree(h->buf.info_i32); cudaFree(h->buf.nsub_i32); cudaFree(h->buf.counters);
   }
   cudaFree(h->params_dev);
+  cudaFree(h->grid_dev);
   cudaFree(h->act_dev);
   cudaFree(h->mask_dev);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -287,7 +365,7 @@ int shipenv_set_params(shipenv_t* h, const ShipEnvParams* params) {
   h->params = *params;
   CUDA_TRY(cudaDeviceSynchronize());   // kernels in flight on any stream may still read the old block
   CUDA_TRY(cudaMemcpy(h->params_dev, params, sizeof(ShipEnvParams), cudaMemcpyHostToDevice));
-  return SHIPENV_OK;
+  return build_grid(h);
 }
 
 int shipenv_construct(shipenv_t* h, const double* init_dev, void* stream) {
@@ -295,13 +373,11 @@ int shipenv_construct(shipenv_t* h, const double* init_dev, void* stream) {
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  rc = (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-           ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, nullptr, init_dev, 0, 1, st)
-           : launch_reset<SHIPENV_MODEL_DETAILED>(h, nullptr, init_dev, 0, 1, st);
+  rc = launch_reset(h, nullptr, init_dev, 0, 1, st);
   if (rc) return rc;
-  senv::k_init_prev_states<<<(int)((h->num_envs + 255) / 256), 256, 0, st>>>(view(h));
-  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(senv_strict::launch_init_prev(view(h), st));
   h->constructed = true;
+  h->init_dev = init_dev;
   return SHIPENV_OK;
 }
 
@@ -315,9 +391,7 @@ int shipenv_reset(shipenv_t* h, const uint8_t* mask_dev, const double* init_dev,
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-             ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, mask_dev, init_dev, 1, 1, st)
-             : launch_reset<SHIPENV_MODEL_DETAILED>(h, mask_dev, init_dev, 1, 1, st);
+  return launch_reset(h, mask_dev, init_dev, 1, 1, st);
 }
 
 int shipenv_init_step(shipenv_t* h, void* stream) {
@@ -325,9 +399,7 @@ int shipenv_init_step(shipenv_t* h, void* stream) {
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-             ? launch_reset<SHIPENV_MODEL_SIMPLE>(h, nullptr, nullptr, 1, 0, st)
-             : launch_reset<SHIPENV_MODEL_DETAILED>(h, nullptr, nullptr, 1, 0, st);
+  return launch_reset(h, nullptr, nullptr, 1, 0, st);
 }
 
 int shipenv_step(shipenv_t* h, const double* actions_dev, void* stream) {
@@ -338,9 +410,7 @@ int shipenv_step(shipenv_t* h, const double* actions_dev, void* stream) {
   if (!actions_dev) return fail(SHIPENV_E_ARG, "actions_dev is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-             ? launch_env<SHIPENV_MODEL_SIMPLE, senv::MODE_STEP>(h, actions_dev, 0, st)
-             : launch_env<SHIPENV_MODEL_DETAILED, senv::MODE_STEP>(h, actions_dev, 0, st);
+  return launch_env(h, 0, actions_dev, 0, st);
 }
 
 int shipenv_substeps(shipenv_t* h, int k, void* stream) {
@@ -349,9 +419,7 @@ int shipenv_substeps(shipenv_t* h, int k, void* stream) {
   if (k < 0) return fail(SHIPENV_E_ARG, "k must be >= 0");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  return (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-             ? launch_env<SHIPENV_MODEL_SIMPLE, senv::MODE_SUBSTEPS>(h, nullptr, k, st)
-             : launch_env<SHIPENV_MODEL_DETAILED, senv::MODE_SUBSTEPS>(h, nullptr, k, st);
+  return launch_env(h, 1, nullptr, k, st);
 }
 
 int shipenv_ship_rollout(shipenv_t* h, int k, void* stream) {
@@ -360,11 +428,9 @@ int shipenv_ship_rollout(shipenv_t* h, int k, void* stream) {
   if (k < 0) return fail(SHIPENV_E_ARG, "k must be >= 0");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->params.ship[0].model_kind == SHIPENV_MODEL_SIMPLE)
-    senv::k_ship_rollout<SHIPENV_MODEL_SIMPLE><<<ship_grid(h), kBlock, 0, st>>>(view(h), k);
-  else
-    senv::k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(h), kBlock, 0, st>>>(view(h), k);
-  CUDA_TRY(cudaGetLastError());
+  const int model = h->params.ship[0].model_kind;
+  CUDA_TRY((h->params.math_mode == SHIPENV_MATH_FAST) ? senv_fast::launch_rollout(view(h), model, k, st)
+                                                      : senv_strict::launch_rollout(view(h), model, k, st));
   return SHIPENV_OK;
 }
 
@@ -381,7 +447,7 @@ int shipenv_reset_host(shipenv_t* h, const uint8_t* mask_host, float* obs_host) 
     CUDA_TRY(cudaMemcpyAsync(h->mask_dev, pv.mask, (size_t)h->num_envs, cudaMemcpyHostToDevice, h->stream));
     mask_dev = h->mask_dev;
   }
-  rc = shipenv_reset(h, mask_dev, nullptr, h->stream);
+  rc = shipenv_reset(h, mask_dev, h->init_dev, h->stream);
   if (rc) return rc;
   return fetch_outputs(h, obs_host, nullptr, nullptr, nullptr);
 }
@@ -442,7 +508,7 @@ int shipenv_measure_fp64_peak(int device, int repeats, double* tflops_out) {
   if (repeats < 1) repeats = 1;
   for (int r = 0; r < repeats + 1; ++r) {          // first launch is the warm-up
     CUDA_TRY(cudaEventRecord(e0));
-    senv::k_dfma_peak<<<blocks, threads>>>(out, iters, 0.9999999, 1e-7);
+    k_dfma_peak<<<blocks, threads>>>(out, iters, 0.9999999, 1e-7);
     CUDA_TRY(cudaEventRecord(e1));
     CUDA_TRY(cudaEventSynchronize(e1));
     float ms = 0.f;

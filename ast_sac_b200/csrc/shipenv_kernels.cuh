@@ -19,17 +19,29 @@
 #include <stdint.h>
 
 #include "shipenv.h"
+#include "shipenv_launch.h"
 
-namespace senv {
+// This header is compiled twice (kernels_strict.cu / kernels_fast.cu):
+//   SENV_NS         namespace of the instantiation
+//   SENV_FAST_MATH  0: the reference's formulas statement by statement, compiled with -fmad=false;
+//                   1: algebraically identical rewrites that drop transcendental calls (wind force
+//                      without atan2/sincos/sin, relative-wind angle by the angle-difference identity),
+//                      compiled with FMA contraction.  Both meet the same parity tests.
+#ifndef SENV_NS
+#error "define SENV_NS and SENV_FAST_MATH before including shipenv_kernels.cuh"
+#endif
+
+#ifndef SENV_MIN_BLOCKS
+#define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
+#endif
+
+namespace SENV_NS {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr double kPi = 3.141592653589793;
 
-struct DevView {
-  const ShipEnvParams* params;
-  ShipEnvBuffers buf;
-  long long num_envs;
-};
+using MapGrid = SenvGrid;
+using DevView = SenvView;
 
 enum Mode { MODE_STEP = 0, MODE_SUBSTEPS = 1 };
 
@@ -108,7 +120,11 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   double rudder;
   {
     const double error = (heading_ref + (-0.0)) - s.yaw;
+#if SENV_FAST_MATH
+    const double d_error = (error - s.hdg_prev_err) * P.inv_ctrl_dt;
+#else
     const double d_error = (error - s.hdg_prev_err) / P.ctrl_dt;
+#endif
     const double error_i = s.hdg_err_i + error * P.ctrl_dt;
     s.hdg_prev_err = error;
     s.hdg_err_i = error_i;
@@ -119,7 +135,11 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   double cmd;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
     const double error = P.desired_speed - s.u;
+#if SENV_FAST_MATH
+    const double d_error = (error - s.spd_aux) * P.inv_ctrl_dt;
+#else
     const double d_error = (error - s.spd_aux) / P.ctrl_dt;
+#endif
     const double error_i = s.spd_err_i + error * P.ctrl_dt;
     s.spd_aux = error;
     s.spd_err_i = error_i;
@@ -170,7 +190,22 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double u_r = u - u_c, v_r = v - v_c;
   const double f_rudder_v = -P.c_rudder_v * rudder * (u - u_c);
   const double f_rudder_r = -P.c_rudder_r * rudder * (u - u_c);
-  // --- wind
+  // --- wind (get_wind_force, ship_model.py:162-175)
+#if SENV_FAST_MATH
+  // u_rw = ws*cos(wd - psi) - u, v_rw = ws*sin(wd - psi) - v with the angle-difference identity;
+  // gamma = -atan2(v_rw, u_rw)  =>  cos(gamma) = u_rw/|V|, sin(gamma) = -v_rw/|V|,
+  // sin(2 gamma) = -2 u_rw v_rw/|V|^2, so with q = 0.6 |V|^2:
+  //   tau_u = q*(-0.5 cos g)*A_f = -0.3 A_f |V| u_rw,  tau_v = q*(0.7 sin g)*A_l = -0.42 A_l |V| v_rw,
+  //   tau_n = q*(0.08 sin 2g)*A_l*L = -0.096 A_l L u_rw v_rw
+  const double cw = P.cos_wind_dir * cpsi + P.sin_wind_dir * spsi;
+  const double sw = P.sin_wind_dir * cpsi - P.cos_wind_dir * spsi;
+  const double u_rw = P.wind_speed * cw - u;
+  const double v_rw = P.wind_speed * sw - v;
+  const double vmag = sqrt(u_rw * u_rw + v_rw * v_rw);
+  const double tau_u = (-0.3 * P.proj_area_f) * vmag * u_rw;
+  const double tau_v = (-0.42 * P.proj_area_l) * vmag * v_rw;
+  const double tau_n = (-0.096 * P.proj_area_l * P.l_ship) * u_rw * v_rw;
+#else
   double sw, cw;
   sincos(P.wind_dir - s.yaw, &sw, &cw);
   const double u_rw = P.wind_speed * cw - u;
@@ -186,6 +221,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double tau_u = tau_coeff * c_x * P.proj_area_f;
   const double tau_v = tau_coeff * c_y * P.proj_area_l;
   const double tau_n = tau_coeff * c_n * P.proj_area_l * P.l_ship;
+#endif
   // --- kinetics (x_g = 0, diagonal mass matrix)
   const double m = P.mass;
   const double crb0 = (-m * v) * r;
@@ -225,44 +261,62 @@ struct MapView {
   const int* start;
   const double* bbox;   // [n_poly][4] = min_e, max_e, min_n, max_n (shared memory)
   int n_poly;
+  MapGrid grid;
 };
 
-__device__ __forceinline__ bool map_contains(const MapView& mp, double n_pos, double e_pos) {
-  const double x = e_pos, y = n_pos;
-  for (int p = 0; p < mp.n_poly; ++p) {
-    const double* bb = mp.bbox + 4 * p;
-    // a point outside the polygon's bounding box crosses an even number of edges: skip (exact)
-    if (x < bb[0] || x > bb[1] || y < bb[2] || y > bb[3]) continue;
-    const int a = mp.start[p], b = mp.start[p + 1];
-    bool inside = false;
-    double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
-    for (int i = a; i < b; ++i) {
-      const double xi = mp.ve[i], yi = mp.vn[i];
-      if ((yi > y) != (yj > y)) {
-        if (x < (xj - xi) * (y - yi) / (yj - yi) + xi) inside = !inside;
-      }
-      xj = xi; yj = yi;
+// bits 0..15: candidate polygons for contains(); bits 16..31: candidates for the clipped distance
+__device__ __forceinline__ unsigned map_cell_masks(const MapView& mp, double n_pos, double e_pos) {
+  const unsigned all = (mp.n_poly >= 16) ? 0xffffu : ((1u << mp.n_poly) - 1u);
+  const double fx = (e_pos - mp.grid.e0) * mp.grid.inv_cell;
+  const double fy = (n_pos - mp.grid.n0) * mp.grid.inv_cell;
+  // outside the grid (or NaN): fall back to every polygon
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < (double)mp.grid.nx && fy < (double)mp.grid.ny)) return all | (all << 16);
+  return __ldg(mp.grid.cells + (int)fy * mp.grid.nx + (int)fx);
+}
+
+// Polygon.contains(Point(x, y)) for one polygon: even-odd crossing rule
+__device__ __forceinline__ bool poly_contains(const MapView& mp, int p, double x, double y) {
+  const double* bb = mp.bbox + 4 * p;
+  // a point outside the polygon's bounding box crosses an even number of edges (exact skip)
+  if (x < bb[0] || x > bb[1] || y < bb[2] || y > bb[3]) return false;
+  const int a = mp.start[p], b = mp.start[p + 1];
+  bool inside = false;
+  double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
+  for (int i = a; i < b; ++i) {
+    const double xi = mp.ve[i], yi = mp.vn[i];
+    if ((yi > y) != (yj > y)) {
+      if (x < (xj - xi) * (y - yi) / (yj - yi) + xi) inside = !inside;
     }
-    if (inside) return true;
+    xj = xi; yj = yi;
+  }
+  return inside;
+}
+
+// PolygonObstacle.if_pos_inside_obstacles (obstacle.py:126-129) over the polygons in `mask`
+__device__ __forceinline__ bool map_contains(const MapView& mp, unsigned mask, double n_pos, double e_pos) {
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (poly_contains(mp, p, e_pos, n_pos)) return true;
   }
   return false;
 }
 
-// min over polygons of ring distance; only its value when <= clip matters to the caller
-// (reward_function.py:386-389, 454-457), so polygons whose bounding box is farther than clip are
-// skipped (exact: they cannot hold the minimum if the minimum is <= clip).
-__device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, double e_pos, double clip) {
+// PolygonObstacle.obstacles_distance (obstacle.py:138-141): min over polygons of the ring distance.
+// Only its value when <= 1000 m matters to the caller (reward_function.py:386-389, 454-457), so
+// polygons farther than that (not in `mask`) are skipped: they cannot hold the minimum if it is
+// <= 1000 m, and if it is not the reward term is 0 either way.
+__device__ __forceinline__ double map_distance(const MapView& mp, unsigned mask, double n_pos, double e_pos) {
   const double px = e_pos, py = n_pos;
   double best2 = INFINITY;
-  for (int p = 0; p < mp.n_poly; ++p) {
-    const double* bb = mp.bbox + 4 * p;
-    const double ddx = fmax(fmax(bb[0] - px, px - bb[1]), 0.0);
-    const double ddy = fmax(fmax(bb[2] - py, py - bb[3]), 0.0);
-    if (ddx > clip + 1.0 || ddy > clip + 1.0) continue;
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
     const int a = mp.start[p], b = mp.start[p + 1];
+    double ax = mp.ve[b - 1], ay = mp.vn[b - 1];
     for (int i = a; i < b; ++i) {
-      const int k = (i + 1 < b) ? i + 1 : a;
-      const double ax = mp.ve[i], ay = mp.vn[i], bx = mp.ve[k], by = mp.vn[k];
+      // ring segment (i-1) -> i; the reference walks i -> i+1, same set of segments
+      const double bx = mp.ve[i], by = mp.vn[i];
       const double dx = bx - ax, dy = by - ay;
       const double l2 = dx * dx + dy * dy;
       double t = 0.0;
@@ -274,15 +328,44 @@ __device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, 
       const double cx = ax + t * dx, cy = ay + t * dy;
       const double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
       best2 = (d2 < best2) ? d2 : best2;
+      ax = bx; ay = by;
     }
   }
   return sqrt(best2);   // sqrt is monotonic and correctly rounded: sqrt(min d2) == min sqrt(d2)
 }
 
-__device__ __forceinline__ bool pos_inside_obstacles(const MapView& mp, double n, double e, double ship_length) {
+// is_pos_inside_obstacles (check_condition.py:48-78): is any of the four corners of the L x L square
+// around the ship inside any polygon.  One pass over a polygon's edges serves all four corners (two
+// distinct y values -> two crossing abscissae per edge, each compared with the two x values).
+__device__ __forceinline__ bool pos_inside_obstacles(const MapView& mp, unsigned mask, double n, double e,
+                                                     double ship_length) {
+  if (mask == 0) return false;
   const double margin = ship_length / 2;
-  const double mn = n - margin, me = e - margin, xn = n + margin, xe = e + margin;
-  return map_contains(mp, mn, me) || map_contains(mp, mn, xe) || map_contains(mp, xn, me) || map_contains(mp, xn, xe);
+  const double y0 = n - margin, x0 = e - margin, y1 = n + margin, x1 = e + margin;
+  while (mask) {
+    const int p = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const double* bb = mp.bbox + 4 * p;
+    // the square misses the polygon's bounding box: every corner crosses an even number of edges
+    if (x1 < bb[0] || x0 > bb[1] || y1 < bb[2] || y0 > bb[3]) continue;
+    const int a = mp.start[p], b = mp.start[p + 1];
+    unsigned in = 0;   // bit 0: (y0,x0)  bit 1: (y0,x1)  bit 2: (y1,x0)  bit 3: (y1,x1)
+    double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
+    for (int i = a; i < b; ++i) {
+      const double xi = mp.ve[i], yi = mp.vn[i];
+      if ((yi > y0) != (yj > y0)) {
+        const double xc = (xj - xi) * (y0 - yi) / (yj - yi) + xi;
+        in ^= (x0 < xc ? 1u : 0u) | (x1 < xc ? 2u : 0u);
+      }
+      if ((yi > y1) != (yj > y1)) {
+        const double xc = (xj - xi) * (y1 - yi) / (yj - yi) + xi;
+        in ^= (x0 < xc ? 4u : 0u) | (x1 < xc ? 8u : 0u);
+      }
+      xj = xi; yj = yi;
+    }
+    if (in) return true;
+  }
+  return false;
 }
 
 __device__ __forceinline__ double py_mod(double a, double b) {   // Python / NumPy float modulo
@@ -459,7 +542,7 @@ __global__ void k_init_prev_states(DevView dv) {
 // the env kernel: step(action) [MODE_STEP] or k x _step() [MODE_SUBSTEPS]
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int ENVKIND, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SENV_MIN_BLOCKS)
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
   __shared__ SharedBlock sb;
   stage_params(sb, dv.params);
@@ -476,7 +559,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
   const bool dynamic_route = IS_IW && role == 1;
   const Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
                  dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * B + env : nullptr, B, P.n_wp};
-  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, G.n_poly};
+  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, G.n_poly, dv.grid};
   const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
   const bool collav_lane = (G.collav == SHIPENV_COLLAV_SIMPLE) && (role == 0 || !IS_IW);
   const double collav_bias = IS_RL ? (-15.0 * (kPi / 180.0)) : (15.0 * (kPi / 180.0));
@@ -547,7 +630,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
       travel_dist = 0.0; travel_time = 0.0;
       have_iw = true;
       // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
-      const bool fail = map_contains(mp, rn, re) ||
+      const bool fail = map_contains(mp, map_cell_masks(mp, rn, re) & 0xffffu, rn, re) ||
                         ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
       if (fail) {
         if (IS_RL) out_reward = (acc_reward >= 0) ? (-acc_reward * 2.0) : (acc_reward * 2.0);
@@ -610,7 +693,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
     double ra = 0.0, rb = 0.0;
     if (stepped) {
       const double len = P.l_ship;
-      const bool grounding = pos_inside_obstacles(mp, s.north, s.east, len);
+      const unsigned cell = map_cell_masks(mp, s.north, s.east);
+      const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
       const double margin = len / 2;
       const bool outside = (s.north < G.map_min_n + margin || s.north > G.map_max_n - margin) ||
                            (s.east < G.map_min_e + margin || s.east > G.map_max_e - margin);
@@ -620,7 +704,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
       if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
       if (IS_RL) {
-        const double gd = map_distance(mp, s.north, s.east, 1000.0);
+        const double gd = map_distance(mp, cell >> 16, s.north, s.east);
         const double aect = fabs(s.e_ct);
         if (role == 0) {
           // test_ship_grounding_reward / test_ship_nav_failure_reward (reward_function.py:359-425)
@@ -830,19 +914,63 @@ k_ship_rollout(DevView dv, int k_steps) {
   if (dv.buf.counters) atomicAdd(&dv.buf.counters[2], (unsigned long long)k_steps);
 }
 
+#ifndef SENV_ONLY_ONE
 // ------------------------------------------------------------------------------------------------
-// DFMA peak microbenchmark (roofline denominator; compiled with explicit fma so -fmad=false does not
-// split it)
+// launch wrappers (declared in shipenv_launch.h)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
-  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-#pragma unroll 4
-  for (int i = 0; i < iters; ++i) {
-    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-  }
-  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-  if (s == 123.456) out[0] = s;   // never true; keeps the chains alive
+constexpr int kBlock = 128;
+
+inline int ship_grid(const DevView& v) { return (int)((2 * v.num_envs + kBlock - 1) / kBlock); }
+
+cudaError_t launch_reset(const SenvView& v, int model, const uint8_t* mask, const double* init, int do_init,
+                         int reinit, cudaStream_t st) {
+  if (model == SHIPENV_MODEL_SIMPLE)
+    k_reset<SHIPENV_MODEL_SIMPLE><<<ship_grid(v), kBlock, 0, st>>>(v, mask, init, do_init, reinit);
+  else
+    k_reset<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, mask, init, do_init, reinit);
+  return cudaGetLastError();
 }
 
-}  // namespace senv
+cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st) {
+  k_init_prev_states<<<(int)((v.num_envs + 255) / 256), 256, 0, st>>>(v);
+  return cudaGetLastError();
+}
+
+template <int MODEL, int MODE>
+static void launch_env_kind(const SenvView& v, int env_kind, const double* actions, int k, cudaStream_t st) {
+  const int grid = ship_grid(v);
+  switch (env_kind) {
+    case SHIPENV_ENV_COLAV_NONIW:
+      k_env<MODEL, SHIPENV_ENV_COLAV_NONIW, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      break;
+    case SHIPENV_ENV_COLAV_IW:
+      k_env<MODEL, SHIPENV_ENV_COLAV_IW, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      break;
+    default:
+      k_env<MODEL, SHIPENV_ENV_RL, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      break;
+  }
+}
+
+cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,
+                       cudaStream_t st) {
+  if (model == SHIPENV_MODEL_SIMPLE) {
+    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_STEP>(v, env_kind, actions, k, st);
+    else launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_SUBSTEPS>(v, env_kind, actions, k, st);
+  } else {
+    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_STEP>(v, env_kind, actions, k, st);
+    else launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_SUBSTEPS>(v, env_kind, actions, k, st);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st) {
+  if (model == SHIPENV_MODEL_SIMPLE) k_ship_rollout<SHIPENV_MODEL_SIMPLE><<<ship_grid(v), kBlock, 0, st>>>(v, k);
+  else k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, k);
+  return cudaGetLastError();
+}
+
+#else
+template __global__ void k_env<0, 1, 0>(DevView, const double*, int);
+#endif
+}  // namespace SENV_NS

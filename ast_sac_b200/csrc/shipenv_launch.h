@@ -1,0 +1,39 @@
+// shipenv_launch.h -- internal interface between the host side of the C ABI (shipenv.cu) and the two
+// builds of the device code (kernels_strict.cu: -fmad=false, kernels_fast.cu: FMA contraction).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "shipenv.h"
+
+// Culling grid over the map bounding box (built on the host at create time, read-only, lives in
+// global memory and stays L1/L2 resident): one 32-bit word per cell; bits 0..15 = polygons that can
+// contain a corner of a ship whose centre lies in the cell, bits 16..31 = polygons whose ring can be
+// within the reward's 1000 m clipping distance of a point in the cell.  Conservative, so the exact
+// tests give the same answers as testing every polygon.
+struct SenvGrid {
+  const unsigned* cells;
+  double e0, n0, inv_cell;
+  int nx, ny;
+};
+
+struct SenvView {
+  const ShipEnvParams* params;
+  ShipEnvBuffers buf;
+  long long num_envs;
+  SenvGrid grid;
+};
+
+#define SENV_DECLARE(ns)                                                                                       \
+  namespace ns {                                                                                               \
+  cudaError_t launch_reset(const SenvView& v, int model, const uint8_t* mask, const double* init, int do_init, \
+                           int reinit, cudaStream_t st);                                                       \
+  cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st);                                            \
+  cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,   \
+                         cudaStream_t st);                                                                     \
+  cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st);                            \
+  }
+
+SENV_DECLARE(senv_strict)
+SENV_DECLARE(senv_fast)

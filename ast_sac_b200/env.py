@@ -34,6 +34,11 @@ from .sim.obstacle import PolygonObstacle
 from .sim.ship_model import BaseShipModel
 from .spaces import Box
 
+# "strict": the reference's formulas statement by statement, no FMA contraction.
+# "fast":   algebraically identical rewrites with fewer transcendental calls + FMA contraction.
+# Both pass the same parity tests (tests/test_gpu_parity.py); see DESIGN.md section 3.
+DEFAULT_MATH_MODE = "fast"
+
 EVENT_STRINGS = [  # reward_function.py:204-262 / get_env_info.py:143-202, env.py:684
     'Ships collision!',
     '|Ship under test experiences grounding!|',
@@ -85,6 +90,7 @@ def pack_ship_params(asset: ShipAssets, nav_fail_tol: float, dt_shaft: Optional[
     p.inv_m_r = 1.0 / (sm.i_z + sm.n_dr)
     p.cur_n, p.cur_e = float(sm.vel_c[0]), float(sm.vel_c[1])
     p.wind_speed, p.wind_dir = sm.wind_speed, sm.wind_dir
+    p.cos_wind_dir, p.sin_wind_dir = float(np.cos(sm.wind_dir)), float(np.sin(sm.wind_dir))
     p.proj_area_f, p.proj_area_l, p.l_ship = sm.proj_area_f, sm.proj_area_l, sm.l_ship
     sc = sm.simulation_config
     p.init_north, p.init_east, p.init_yaw = sc.initial_north_position_m, sc.initial_east_position_m, sc.initial_yaw_angle_rad
@@ -94,6 +100,7 @@ def pack_ship_params(asset: ShipAssets, nav_fail_tol: float, dt_shaft: Optional[
     ap = asset.auto_pilot
     pid = ap.heading_controller.ship_heading_controller
     p.ctrl_dt = pid.time_step
+    p.inv_ctrl_dt = 1.0 / pid.time_step
     p.hdg_kp, p.hdg_kd, p.hdg_ki = pid.kp, pid.kd, pid.ki
     p.max_rudder = ap.heading_controller.max_rudder_angle
     nav = ap.navigate
@@ -144,7 +151,8 @@ def pack_ship_params(asset: ShipAssets, nav_fail_tol: float, dt_shaft: Optional[
     return p
 
 
-def pack_params(assets, map_obj: PolygonObstacle, args, env_kind: int, post_reset: bool) -> L.Params:
+def pack_params(assets, map_obj: PolygonObstacle, args, env_kind: int, post_reset: bool,
+                math_mode: int = L.MATH_STRICT) -> L.Params:
     if len(assets) != 2:
         raise ValueError("assets must be [ship under test, obstacle ship]")
     P = L.Params()
@@ -195,6 +203,7 @@ def pack_params(assets, map_obj: PolygonObstacle, args, env_kind: int, post_rese
         raise ValueError(f"unknown collav_mode {collav!r}")
     P.max_sampling_frequency = msf
     P.abi_version = L.ABI_VERSION
+    P.math_mode = math_mode
     return P
 
 
@@ -206,8 +215,14 @@ class BatchedShipEnv:
     OBS_DIM = 8
 
     def __init__(self, assets: List[ShipAssets], map: PolygonObstacle, args, num_envs: int = 1,
-                 device: Union[None, int, str, torch.device] = None, init_states: Optional[torch.Tensor] = None):
+                 device: Union[None, int, str, torch.device] = None, init_states: Optional[torch.Tensor] = None,
+                 math_mode: Union[str, int, None] = None):
         self.args = args
+        if math_mode is None:
+            math_mode = getattr(args, "math_mode", DEFAULT_MATH_MODE)
+        self.math_mode = {"strict": L.MATH_STRICT, "fast": L.MATH_FAST}.get(math_mode, math_mode)
+        if self.math_mode not in (L.MATH_STRICT, L.MATH_FAST):
+            raise ValueError("math_mode must be 'strict' or 'fast'")
         self.collav = args.collav_mode
         self.assets = assets
         [self.test, self.obs] = self.assets
@@ -263,7 +278,7 @@ class BatchedShipEnv:
 
     def _open(self):
         lib = L.load()
-        self._params = pack_params(self.assets, self.map, self.args, self.ENV_KIND, self._post_reset)
+        self._params = pack_params(self.assets, self.map, self.args, self.ENV_KIND, self._post_reset, self.math_mode)
         h = C.c_void_p()
         L.check(lib.shipenv_create(C.byref(self._params), self.num_envs, self._device.index, C.byref(h)))
         self._handle = h
@@ -414,7 +429,7 @@ class BatchedShipEnv:
             self._post_reset = True
             if self._params.ship[0].model_kind == L.MODEL_DETAILED:
                 # the first reset() leaves the machinery integrator at dt = 0.01 (ship_engine.py:331-333)
-                self._params = pack_params(self.assets, self.map, self.args, self.ENV_KIND, True)
+                self._params = pack_params(self.assets, self.map, self.args, self.ENV_KIND, True, self.math_mode)
                 L.check(lib.shipenv_set_params(self._handle, C.byref(self._params)))
         mask_ptr = None
         if mask is not None:

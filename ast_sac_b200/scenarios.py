@@ -166,18 +166,19 @@ def build_colav_assets(args, iw=True, test_init=None, obs_init=None, sim_time=10
     return [test, obs], PolygonObstacle(MAP_DATA)
 
 
-def prepare_multiship_rl_env(args, num_envs=1, device=None, mode="PTI", init_states=None, **kw):
+def prepare_multiship_rl_env(args, num_envs=1, device=None, mode="PTI", init_states=None, math_mode=None, **kw):
     """Drop-in for run/env_setup.py:prepare_multiship_rl_env -> (env, assets)."""
     assets, map_obj = build_rl_assets(args, mode=mode, **kw)
     env = MultiShipRLEnv(assets=assets, map=map_obj, args=args, num_envs=num_envs, device=device,
-                         init_states=init_states)
+                         init_states=init_states, math_mode=math_mode)
     return env, assets
 
 
-def prepare_colav_env(args, iw=True, num_envs=1, device=None, init_states=None, **kw):
+def prepare_colav_env(args, iw=True, num_envs=1, device=None, init_states=None, math_mode=None, **kw):
     assets, map_obj = build_colav_assets(args, iw=iw, **kw)
     cls = MultiShipEnv if iw else MultiShipNonIWEnv
-    env = cls(assets=assets, map=map_obj, args=args, num_envs=num_envs, device=device, init_states=init_states)
+    env = cls(assets=assets, map=map_obj, args=args, num_envs=num_envs, device=device, init_states=init_states,
+              math_mode=math_mode)
     return env, assets
 
 

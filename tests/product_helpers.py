@@ -9,7 +9,7 @@ from ast_sac_b200 import scenarios as S
 from ast_sac_b200 import _lib as L
 
 
-def env_from_meta(meta, num_envs=1, init_states=None, device=None):
+def env_from_meta(meta, num_envs=1, init_states=None, device=None, math_mode=None):
     """Build the product env for a golden fixture's ``meta`` (see tests/golden/make_golden.py)."""
     if isinstance(meta, (bytes, str, np.ndarray)):
         meta = json.loads(str(meta))
@@ -17,12 +17,14 @@ def env_from_meta(meta, num_envs=1, init_states=None, device=None):
     kw = dict(test_init=meta.get("test_init"), obs_init=meta.get("obs_init"))
     if meta["kind"] == "rl":
         return S.prepare_multiship_rl_env(args, num_envs=num_envs, mode=meta.get("mode", "PTI"), device=device,
-                                          init_states=init_states, sim_time=meta.get("sim_time", 10000), **kw)
+                                          init_states=init_states, sim_time=meta.get("sim_time", 10000),
+                                          math_mode=math_mode, **kw)
     if meta["kind"] == "colav":
         return S.prepare_colav_env(args, iw=True, num_envs=num_envs, device=device, init_states=init_states,
-                                   sim_time=meta.get("sim_time", 10000), **kw)
+                                   sim_time=meta.get("sim_time", 10000), math_mode=math_mode, **kw)
     if meta["kind"] == "noniw":
-        return S.prepare_colav_env(args, iw=False, num_envs=num_envs, device=device, init_states=init_states, **kw)
+        return S.prepare_colav_env(args, iw=False, num_envs=num_envs, device=device, init_states=init_states,
+                                   math_mode=math_mode, **kw)
     raise ValueError(meta["kind"])
 
 
