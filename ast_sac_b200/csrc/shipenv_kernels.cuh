@@ -598,7 +598,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
   s.n_wp = P.n_wp + n_iw;
 
   // outputs of this call
-  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f, o4 = 0.f;      // this lane's next_states entries
+  double u_pre = 0.0;         // surge speed before the last integration (obs[6])
+  bool last_stop_branch = false;
   double out_reward = 0.0;
   int out_info = 0, nsub = 0;
   bool have_obs = false;      // next_observations was assigned by this call
@@ -649,7 +650,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
   // ---------------- simulator loop
   while (__any_sync(FULL_MASK, !finished)) {
     bool stepped = false, st_done = false, st_terminal = false, st_roa = false;
-    double u_pre = 0.0;
     if (!finished) {
       stepped = true;
       const double dt = P.dt;
@@ -657,9 +657,10 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
         // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
         s.time = s.time + dt;
         s.time = s.time + dt;
-        o0 = (float)s.north; o1 = (float)s.east; o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct;
+        last_stop_branch = true;
       } else {
         u_pre = s.u;
+        last_stop_branch = false;
         bool hit = false;
         if (collav_lane) {
           // is_collision_imminent on the float32 self.states (check_condition.py:130-140)
@@ -668,17 +669,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
         }
         const double pre_n = s.north, pre_e = s.east;
         ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias);
-        o0 = (float)s.north; o1 = (float)s.east;
         if (role == 1 && IS_IW) {
-          o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct;
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
             const double tn = pre_n - log_n, te = pre_e - log_e;
             travel_dist += sqrt(tn * tn + te * te);
             travel_time += dt;
           }
-        } else {
-          o2 = (float)s.e_ct;
         }
         log_n = pre_n; log_e = pre_e;
       }
@@ -699,7 +696,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
       const bool outside = (s.north < G.map_min_n + margin || s.north > G.map_max_n - margin) ||
                            (s.east < G.map_min_e + margin || s.east > G.map_max_e - margin);
       const double dn = s.north - route_end_n, de = s.east - route_end_e;
-      const bool reached = sqrt(dn * dn + de * de) <= 200.0;
+      // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
+      // sqrt(nextafter(40000)) rounds above 200)
+      const bool reached = (dn * dn + de * de) <= 40000.0;
       bool nav_fail = fabs(s.e_ct) > P.nav_fail_tol;
       if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
@@ -841,6 +840,14 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
   }
 
   // ---------------- epilogue: observation row, outputs, state write-back
+  // this lane's entries of next_states (test_step / obs_step return values, env.py:440-443, 472-477,
+  // 519-524): stop branch and the obstacle ship of the IW envs return [N, E, psi, u, e_ct], the others
+  // [N, E, e_ct]
+  const float o0 = (float)s.north, o1 = (float)s.east;
+  float o2, o3 = 0.f, o4 = 0.f;
+  if (last_stop_branch) { o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct; }
+  else if (role == 1 && IS_IW) { o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct; }
+  else { o2 = (float)s.e_ct; }
   const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
   const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
   const float t2 = __shfl_xor_sync(FULL_MASK, o2, 1);

@@ -40,7 +40,7 @@ N_RL_STEPS = 9
 #    ncu capture under profiles/ (includes the CUDA math library's sin/cos/atan2/exp internals and
 #    the map-geometry tests); filled in from profiles/r01_ncu_summary.md.
 FLOP_ALGO = {"colav_iw": 370.0 + 26.0, "rl": 450.0 + 31.0}
-FLOP_EXEC = {"colav_iw": 4200.0, "rl": 6200.0}
+FLOP_EXEC = {"colav_iw": 599.0, "rl": 1150.0}     # profiles/r01_ncu_summary.md section 2 (fast build)
 # HBM bytes per env-step when every simulator step is its own launch (K = 1): DESIGN.md section 4
 BYTES_K1 = 2 * (2 * (14 * 8 + 4) + 7 * 8 + 3 * 4) + 32 + 8 + 4 + 4
 
@@ -227,11 +227,14 @@ def run_b200(a, rank, local_rank, world):
     ep_rl = torch.zeros(B, dtype=torch.int32, device=dev)
     ep_steps = torch.zeros(B, dtype=torch.int32, device=dev)
 
+    launch_steps = torch.zeros(1 + N_RL_STEPS, dtype=torch.int64, device=dev)
+
     def one_episode(events=None):
         """reset + 9 step() on device-resident actions; returns list of (start, end) event pairs."""
         ep_return.zero_()
         ep_rl.zero_()
         ep_steps.zero_()
+        launch_steps.zero_()
         pairs = []
         for j in range(-1, N_RL_STEPS):
             if events is not None:
@@ -248,6 +251,7 @@ def run_b200(a, rank, local_rank, world):
                 ep_return.add_(env.reward_buf)
                 ep_rl.add_((env.nsub_buf > 0).to(torch.int32))
                 ep_steps.add_(env.nsub_buf)
+                launch_steps[j + 1] = env.nsub_buf.sum()
         return pairs
 
     for _ in range(a.warmup):
@@ -368,6 +372,7 @@ def run_b200(a, rank, local_rank, world):
             "clocks": clocks,
             "gpu_launches": int(a.steps * (1 + N_RL_STEPS)),
             "launch_ms_mean": [round(float(x), 4) for x in launch_ms.mean(axis=0)],
+            "launch_env_steps": [int(x) for x in launch_steps.tolist()],
             "roofline": roofline, "roofline_hbm_k1": roofline_k1,
             "episode_stats": PAR.summarise(gathered),
         }
