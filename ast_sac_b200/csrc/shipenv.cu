@@ -44,6 +44,10 @@ struct shipenv {
   bool owns = false;
   bool constructed = false;
   const double* init_dev = nullptr;   // per-ship initial states given to shipenv_construct (caller-owned)
+  unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch
+  unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
+  int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
+  int sm_count = 0;
   unsigned* grid_dev = nullptr;       // culling grid cells
   SenvGrid grid{};
   // staging for the *_host entry points
@@ -110,10 +114,19 @@ int launch_reset(shipenv* h, const uint8_t* mask, const double* init, int do_ini
 
 int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t st) {
   const int model = h->params.ship[0].model_kind;
+  // Grid policy.  With every environment alive a static grid (one slot per environment) is fastest;
+  // once a noticeable share is done, a persistent grid whose lane pairs refill from the work queue
+  // wins (finished environments cost one fetch instead of an idle lane pair).  The share comes from the
+  // previous launch's count (copied to pinned memory without a sync, so it may lag by a launch).
+  int persistent = h->persist_mode;
+  if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
-                      ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, st)
-                      : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, st);
+                      ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
+                                              h->sm_count, persistent, st)
+                      : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
+                                                h->sm_count, persistent, st);
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(h->done_host, h->queue_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   return SHIPENV_OK;
 }
 
@@ -269,11 +282,18 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
     return fail(SHIPENV_E_CUDA, "uploading parameters: %s", cudaGetErrorString(ce));
   }
   rc = build_grid(h);
+  if (rc == SHIPENV_OK && (cudaMalloc(&h->queue_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+                           cudaMallocHost(&h->done_host, sizeof(unsigned long long)) != cudaSuccess))
+    rc = fail(SHIPENV_E_CUDA, "allocating the work-queue counters failed");
   if (rc) {
     cudaFree(h->params_dev);
+    cudaFree(h->grid_dev);
     delete h;
     return rc;
   }
+  *h->done_host = 0;
+  if (const char* pm = getenv("SHIPENV_PERSISTENT")) h->persist_mode = atoi(pm);   // -1 auto (default), 0, 1
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return SHIPENV_OK;
 }
@@ -288,6 +308,8 @@ int shipenv_destroy(shipenv_t* h) {
   }
   cudaFree(h->params_dev);
   cudaFree(h->grid_dev);
+  cudaFree(h->queue_dev);
+  if (h->done_host) cudaFreeHost(h->done_host);
   cudaFree(h->act_dev);
   cudaFree(h->mask_dev);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -391,6 +413,7 @@ int shipenv_reset(shipenv_t* h, const uint8_t* mask_dev, const double* init_dev,
   }
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (!mask_dev) *h->done_host = 0;
   return launch_reset(h, mask_dev, init_dev, 1, 1, st);
 }
 

@@ -31,6 +31,10 @@
 #error "define SENV_NS and SENV_FAST_MATH before including shipenv_kernels.cuh"
 #endif
 
+#ifndef SENV_REFILL_MIN
+#define SENV_REFILL_MIN 1   // lane pairs of a warp that must be free before they fetch (1 = fetch at once;
+                            // batching 2/4/8 measured slower: 9.63 / 9.87 / 11.5 ms vs 9.35 ms per episode)
+#endif
 #ifndef SENV_MIN_BLOCKS
 #define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
 #endif
@@ -540,118 +544,163 @@ __global__ void k_init_prev_states(DevView dv) {
 
 // ------------------------------------------------------------------------------------------------
 // the env kernel: step(action) [MODE_STEP] or k x _step() [MODE_SUBSTEPS]
+//
+// Persistent grid with lane-pair refill: the grid is sized to what is resident on the GPU; every lane
+// pair first takes the environment with its own slot index and, whenever its environment has finished
+// the call (reached the next radius of acceptance, terminated, was already done, ...), stores it and
+// pulls the next environment index from a device-wide counter (one warp-aggregated atomicAdd).  A warp
+// therefore keeps all 16 pairs busy until the queue is empty instead of waiting for its slowest
+// environment, and environments that are already done cost one fetch.
 // ------------------------------------------------------------------------------------------------
+enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
+
 template <int MODEL, int ENVKIND, int MODE>
 __global__ void __launch_bounds__(128, SENV_MIN_BLOCKS)
-k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
+k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
   __shared__ SharedBlock sb;
   stage_params(sb, dv.params);
   const ShipEnvParams& G = sb.p;
   const long long B = dv.num_envs;
   const long long n_ships = 2 * B;
-  const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool valid = sidx < n_ships;
-  const long long env = valid ? (sidx >> 1) : 0;
+  const long long n_slots = ((long long)gridDim.x * blockDim.x) >> 1;
+  const int lane = (int)(threadIdx.x & 31);
   const int role = (int)(threadIdx.x & 1);
   const ShipEnvShipParams& P = G.ship[role];
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
   const bool dynamic_route = IS_IW && role == 1;
-  const Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
-                 dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * B + env : nullptr, B, P.n_wp};
   const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, G.n_poly, dv.grid};
   const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
   const bool collav_lane = (G.collav == SHIPENV_COLLAV_SIMPLE) && (role == 0 || !IS_IW);
   const double collav_bias = IS_RL ? (-15.0 * (kPi / 180.0)) : (15.0 * (kPi / 180.0));
   const double route_end_n = P.wp_north[P.n_wp - 1], route_end_e = P.wp_east[P.n_wp - 1];
 
-  Ship s;
+  long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  int lstate = (env < B) ? LS_LOAD : LS_IDLE;
+
+  // registers of the environment currently held by this lane
+  Ship s = Ship{};
+  s.k = 1;
+  Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp};
   double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0, n_base = 0.0, e_base = 0.0;
   double log_n = 0.0, log_e = 0.0;
-  int sampling_count = 0, snapshot_info = 0, flags = 0;
+  int sampling_count = 0, snapshot_info = 0, flags = 0, n_iw = 0;
   float ps_tn = 0.f, ps_te = 0.f, ps_on = 0.f, ps_oe = 0.f;
-  bool finished = true;
-  if (valid) {
-    load_ship(dv, n_ships, sidx, s);
-    const double* ef = dv.buf.env_f64;
-    travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
-    travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
-    acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
-    n_base = ef[SHIPENV_EF_N_BASE * B + env];
-    e_base = ef[SHIPENV_EF_E_BASE * B + env];
-    log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
-    log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
-    const int* ei = dv.buf.env_i32;
-    sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
-    snapshot_info = ei[SHIPENV_EI_SNAPSHOT_INFO * B + env];
-    flags = ei[SHIPENV_EI_FLAGS * B + env];
-    if (G.collav == SHIPENV_COLLAV_SIMPLE) {
-      ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
-      ps_on = dv.buf.prev_f32[2 * B + env]; ps_oe = dv.buf.prev_f32[3 * B + env];
-    }
-    finished = (flags & SHIPENV_FLAG_DONE) != 0;
-  } else {
-    s = Ship{};
-    s.k = 1;
-  }
-  int n_iw = dynamic_route ? sampling_count : 0;
-  s.n_wp = P.n_wp + n_iw;
-
-  // outputs of this call
   double u_pre = 0.0;         // surge speed before the last integration (obs[6])
   bool last_stop_branch = false;
   double out_reward = 0.0;
   int out_info = 0, nsub = 0;
   bool have_obs = false;      // next_observations was assigned by this call
-  bool write_snapshot_only = false;
   int stage = 0;              // MODE_STEP: 0 main loop, 1 extra step after RoA, 2 run to completion
   bool have_iw = false;
-  int k_left = k_substeps;
+  int k_left = 0;
+  // metric counters over every environment this lane handled
+  int total_sub = 0, total_fin = 0, total_dead = 0;
 
-  if (MODE == MODE_STEP && !finished) {
-    // ---------------- step(action) prologue: rl_env env.py:641-696, run_colav env.py:1430-1474
-    if (sampling_count < G.max_sampling_frequency) {
-      const double a = actions[env];
-      sampling_count += 1;
-      // get_intermediate_waypoints (env.py:198-236)
-      const double l_s = fabs(G.ab_segment_length * tan(a));
-      double e_s = l_s * G.cos_omega;
-      double n_s = l_s * G.sin_omega;
-      if (a > 0) e_s *= -1; else n_s *= -1;
-      const double rn = n_base + n_s, re = e_base + e_s;
-      n_base = rn + G.ab_north_segment_length;
-      e_base = re + G.ab_east_segment_length;
-      if (role == 1) {
-        // update_route: insert before the last waypoint (controllers.py:417-422)
-        dv.buf.iw_f64[(long long)(sampling_count - 1) * B + env] = rn;
-        dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + sampling_count - 1) * B + env] = re;
-        n_iw = sampling_count;
-        s.n_wp = P.n_wp + n_iw;
+  for (;;) {
+    // ---------------- (1) fetch: lane pairs without an environment pull the next index
+    {
+      unsigned want = __ballot_sync(FULL_MASK, lstate == LS_FETCH && role == 0);
+      if (SENV_REFILL_MIN > 1) {   // optional batching of refills
+        const unsigned busy = __ballot_sync(FULL_MASK, lstate == LS_RUN || lstate == LS_LOAD);
+        if (__popc(want) < SENV_REFILL_MIN && busy != 0) want = 0;
       }
-      travel_dist = 0.0; travel_time = 0.0;
-      have_iw = true;
-      // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
-      const bool fail = map_contains(mp, map_cell_masks(mp, rn, re) & 0xffffu, rn, re) ||
-                        ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
-      if (fail) {
-        if (IS_RL) out_reward = (acc_reward >= 0) ? (-acc_reward * 2.0) : (acc_reward * 2.0);
-        snapshot_info = (snapshot_info & 0x7ff) | SHIPENV_EV_SAMPLING_FAILURE | SHIPENV_INFO_TERMINAL;
-        out_info = snapshot_info | SHIPENV_INFO_DONE;
-        flags |= SHIPENV_FLAG_DONE;
-        write_snapshot_only = true;      // obs row (the snapshot) is returned unchanged
-        finished = true;
-      } else if (IS_RL) {
-        acc_reward = 0.0;
+      if (want) {
+        const int leader = __ffs(want) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(want));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        long long mine = n_slots + (long long)base + __popc(want & ((1u << lane) - 1u));
+        mine = __shfl_sync(FULL_MASK, mine, lane & ~1);       // the obstacle lane takes its partner's index
+        if (lstate == LS_FETCH) {
+          env = mine;
+          lstate = (env < B) ? LS_LOAD : LS_IDLE;
+        }
       }
     }
-  }
-  if (valid) refresh_segment(rt, n_iw, s);
+    if (!__any_sync(FULL_MASK, lstate != LS_IDLE)) break;
 
-  // ---------------- simulator loop
-  while (__any_sync(FULL_MASK, !finished)) {
-    bool stepped = false, st_done = false, st_terminal = false, st_roa = false;
-    if (!finished) {
-      stepped = true;
+    // ---------------- (2) load the environment and run the step(action) prologue
+    bool finalize = false;                // store this environment at the end of the iteration
+    bool write_snapshot_only = false;
+    if (lstate == LS_LOAD) {
+      const long long sidx = 2 * env + role;
+      load_ship(dv, n_ships, sidx, s);
+      const double* ef = dv.buf.env_f64;
+      travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
+      travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
+      acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
+      n_base = ef[SHIPENV_EF_N_BASE * B + env];
+      e_base = ef[SHIPENV_EF_E_BASE * B + env];
+      log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
+      log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+      const int* ei = dv.buf.env_i32;
+      sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
+      snapshot_info = ei[SHIPENV_EI_SNAPSHOT_INFO * B + env];
+      flags = ei[SHIPENV_EI_FLAGS * B + env];
+      if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+        ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
+        ps_on = dv.buf.prev_f32[2 * B + env]; ps_oe = dv.buf.prev_f32[3 * B + env];
+      }
+      rt.iw_n = dynamic_route ? dv.buf.iw_f64 + env : nullptr;
+      rt.iw_e = dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * B + env : nullptr;
+      n_iw = dynamic_route ? sampling_count : 0;
+      s.n_wp = P.n_wp + n_iw;
+      u_pre = 0.0; last_stop_branch = false; out_reward = 0.0; out_info = 0; nsub = 0;
+      have_obs = false; stage = 0; have_iw = false; k_left = k_substeps;
+      lstate = LS_RUN;
+      if (flags & SHIPENV_FLAG_DONE) {
+        // already done before this call: nothing changes except the step count of the call
+        if (role == 1) { dv.buf.nsub_i32[env] = 0; total_dead += 1; }
+        lstate = LS_FETCH;
+      } else if (MODE == MODE_SUBSTEPS && k_left <= 0) {
+        if (role == 1) dv.buf.nsub_i32[env] = 0;
+        lstate = LS_FETCH;
+      } else if (MODE == MODE_STEP) {
+        // ---- step(action) prologue: rl_env env.py:641-696, run_colav env.py:1430-1474
+        if (sampling_count < G.max_sampling_frequency) {
+          const double a = actions[env];
+          sampling_count += 1;
+          // get_intermediate_waypoints (env.py:198-236)
+          const double l_s = fabs(G.ab_segment_length * tan(a));
+          double e_s = l_s * G.cos_omega;
+          double n_s = l_s * G.sin_omega;
+          if (a > 0) e_s *= -1; else n_s *= -1;
+          const double rn = n_base + n_s, re = e_base + e_s;
+          n_base = rn + G.ab_north_segment_length;
+          e_base = re + G.ab_east_segment_length;
+          if (role == 1) {
+            // update_route: insert before the last waypoint (controllers.py:417-422)
+            dv.buf.iw_f64[(long long)(sampling_count - 1) * B + env] = rn;
+            dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + sampling_count - 1) * B + env] = re;
+            n_iw = sampling_count;
+            s.n_wp = P.n_wp + n_iw;
+          }
+          travel_dist = 0.0; travel_time = 0.0;
+          have_iw = true;
+          // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
+          const bool fail = map_contains(mp, map_cell_masks(mp, rn, re) & 0xffffu, rn, re) ||
+                            ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
+          if (fail) {
+            if (IS_RL) out_reward = (acc_reward >= 0) ? (-acc_reward * 2.0) : (acc_reward * 2.0);
+            snapshot_info = (snapshot_info & 0x7ff) | SHIPENV_EV_SAMPLING_FAILURE | SHIPENV_INFO_TERMINAL;
+            out_info = snapshot_info | SHIPENV_INFO_DONE;
+            flags |= SHIPENV_FLAG_DONE;
+            write_snapshot_only = true;      // obs row (the snapshot) is returned unchanged
+            finalize = true;
+          } else if (IS_RL) {
+            acc_reward = 0.0;
+          }
+        }
+      }
+      if (lstate == LS_RUN && !finalize) refresh_segment(rt, n_iw, s);
+    }
+
+    // ---------------- (3) simulator steps of the running lanes, until some pair has finished its call
+    do {
+    const bool running = (lstate == LS_RUN) && !finalize;
+    bool st_done = false, st_terminal = false, st_roa = false;
+    if (running) {
       const double dt = P.dt;
       if (has_stop_branch && s.stop) {
         // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
@@ -688,7 +737,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
     // own partial flags / rewards
     int my_flags = 0;
     double ra = 0.0, rb = 0.0;
-    if (stepped) {
+    if (running) {
       const double len = P.l_ship;
       const unsigned cell = map_cell_masks(mp, s.north, s.east);
       const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
@@ -720,7 +769,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
     double p_ra = 0.0, p_rb = 0.0;
     if (IS_RL) { p_ra = shfl_xor_f64(ra, 1); p_rb = shfl_xor_f64(rb, 1); }
 
-    if (stepped) {
+    if (running) {
       nsub += 1;
       const double t_n = role == 0 ? s.north : p_north, t_e = role == 0 ? s.east : p_east;
       const double t_yaw = role == 0 ? s.yaw : p_yaw, t_time = role == 0 ? s.time : p_time;
@@ -790,24 +839,23 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
         if (role == 1 && os && !terminal) s.stop = 1;
         // done needs both stop flags: resolved after the shuffle below
       }
-      const int step_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
-                            (os ? SHIPENV_INFO_OBS_STOP : 0);
-      out_info = step_info;
+      out_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
+                 (os ? SHIPENV_INFO_OBS_STOP : 0);
       if (IS_RL) {
         if (MODE == MODE_STEP) acc_reward += r_total;
         out_reward = r_total;
       }
     }
     const int p_stop = __shfl_xor_sync(FULL_MASK, s.stop, 1);
-    if (stepped) {
+    if (running) {
       if (!IS_RL) st_done = s.stop && p_stop;
       const bool combined_done = st_terminal || st_done;
       if (combined_done) out_info |= SHIPENV_INFO_DONE;
       if (MODE == MODE_SUBSTEPS) {
         have_obs = true;
         k_left -= 1;
-        if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
-        else if (k_left <= 0) finished = true;
+        if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
+        else if (k_left <= 0) finalize = true;
       } else {
         // step() control flow: rl_env env.py:700-771, run_colav env.py:1478-1533
         if (stage == 0) {
@@ -815,86 +863,90 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps) {
           // (meaningful on the obstacle lane; the test lane receives it below)
           const double dn = s.north - s.wn, de = s.east - s.we;
           st_roa = (dn * dn + de * de) < G.roa * G.roa;
-          if (combined_done) { have_obs = true; flags |= SHIPENV_FLAG_DONE; finished = true; }
+          if (combined_done) { have_obs = true; flags |= SHIPENV_FLAG_DONE; finalize = true; }
         } else if (stage == 1) {
           have_obs = true;
-          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
+          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
           else if (sampling_count == G.max_sampling_frequency) { travel_dist = 0.0; travel_time = 0.0; stage = 2; }
-          else finished = true;
+          else finalize = true;
         } else {
           have_obs = true;
-          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finished = true; }
+          if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
         }
       }
     }
     if (MODE == MODE_STEP) {
       // RoA flag lives on the obstacle lane (role 1): broadcast it to the pair
-      const int is_roa = __shfl_sync(FULL_MASK, (int)st_roa, (threadIdx.x & 31) | 1);
-      if (stepped && !finished && stage == 0) {
-        if (is_roa) {
-          if (have_iw) stage = 1;
-          else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finished = true; }
+      const int is_roa = __shfl_sync(FULL_MASK, (int)st_roa, lane | 1);
+      if (running && !finalize && stage == 0 && is_roa) {
+        if (have_iw) stage = 1;
+        else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finalize = true; }
+      }
+    }
+    } while (!__any_sync(FULL_MASK, finalize || lstate == LS_FETCH));
+
+    // ---------------- (4) store finished environments and free the lane pair
+    {
+      // this lane's entries of next_states (test_step / obs_step return values, env.py:440-443, 472-477,
+      // 519-524): stop branch and the obstacle ship of the IW envs return [N, E, psi, u, e_ct], the others
+      // [N, E, e_ct]
+      const float o0 = (float)s.north, o1 = (float)s.east;
+      float o2, o3 = 0.f, o4 = 0.f;
+      if (last_stop_branch) { o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct; }
+      else if (role == 1 && IS_IW) { o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct; }
+      else { o2 = (float)s.e_ct; }
+      const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
+      const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
+      const float t2 = __shfl_xor_sync(FULL_MASK, o2, 1);
+      if (finalize) {
+        store_ship(dv, n_ships, 2 * env + role, s);
+        if (role == 1) {
+          if (have_obs) {
+            float4* orow = reinterpret_cast<float4*>(dv.buf.obs_f32 + env * 8);
+            orow[0] = make_float4(t0, t1, t2, o0);
+            orow[1] = IS_IW ? make_float4(o1, o2, o3, o4) : make_float4(o1, o2, 0.f, 0.f);
+            snapshot_info = out_info & ~SHIPENV_INFO_DONE;
+          }
+          double* ef = dv.buf.env_f64;
+          ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
+          ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
+          ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
+          ef[SHIPENV_EF_N_BASE * B + env] = n_base;
+          ef[SHIPENV_EF_E_BASE * B + env] = e_base;
+          ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
+          ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
+          int* ei = dv.buf.env_i32;
+          ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
+          ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot_info;
+          ei[SHIPENV_EI_FLAGS * B + env] = flags;
+          if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+            dv.buf.prev_f32[0 * B + env] = ps_tn; dv.buf.prev_f32[1 * B + env] = ps_te;
+            dv.buf.prev_f32[2 * B + env] = ps_on; dv.buf.prev_f32[3 * B + env] = ps_oe;
+          }
+          if (IS_RL && MODE == MODE_STEP && !write_snapshot_only) out_reward = acc_reward;
+          dv.buf.reward[env] = out_reward;
+          dv.buf.info_i32[env] = out_info;
+          dv.buf.nsub_i32[env] = nsub;
+          total_sub += nsub;
+          if (flags & SHIPENV_FLAG_DONE) total_fin += 1;
         }
+        lstate = LS_FETCH;
       }
     }
   }
 
-  // ---------------- epilogue: observation row, outputs, state write-back
-  // this lane's entries of next_states (test_step / obs_step return values, env.py:440-443, 472-477,
-  // 519-524): stop branch and the obstacle ship of the IW envs return [N, E, psi, u, e_ct], the others
-  // [N, E, e_ct]
-  const float o0 = (float)s.north, o1 = (float)s.east;
-  float o2, o3 = 0.f, o4 = 0.f;
-  if (last_stop_branch) { o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct; }
-  else if (role == 1 && IS_IW) { o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct; }
-  else { o2 = (float)s.e_ct; }
-  const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
-  const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
-  const float t2 = __shfl_xor_sync(FULL_MASK, o2, 1);
-  // metric counters: one atomic per warp (all lanes take part in the reduction)
-  const bool touched = valid && (nsub > 0 || write_snapshot_only);
+  // metric counters: one atomic per warp
   {
-    const int sub = __reduce_add_sync(FULL_MASK, (valid && role == 1) ? nsub : 0);
-    const int fin = __reduce_add_sync(FULL_MASK, (touched && role == 1 && (flags & SHIPENV_FLAG_DONE)) ? 1 : 0);
-    if ((threadIdx.x & 31) == 0 && dv.buf.counters) {
-      if (sub) atomicAdd(&dv.buf.counters[0], (unsigned long long)sub);
-      if (fin) atomicAdd(&dv.buf.counters[1], (unsigned long long)fin);
+    const int sub = __reduce_add_sync(FULL_MASK, total_sub);
+    const int fin = __reduce_add_sync(FULL_MASK, total_fin);
+    const int dead = __reduce_add_sync(FULL_MASK, total_dead);
+    if (lane == 0) {
+      if (dv.buf.counters) {
+        if (sub) atomicAdd(&dv.buf.counters[0], (unsigned long long)sub);
+        if (fin) atomicAdd(&dv.buf.counters[1], (unsigned long long)fin);
+      }
+      if (dead + fin) atomicAdd(&queue[1], (unsigned long long)(dead + fin));   // done after this launch
     }
-  }
-  if (!valid) return;
-  if (!touched) {
-    // environment was already done before this call (or k = 0): state and outputs stay as they are
-    if (role == 1) dv.buf.nsub_i32[env] = 0;
-    return;
-  }
-  store_ship(dv, n_ships, sidx, s);
-  if (role == 1) {
-    if (have_obs) {
-      float4* orow = reinterpret_cast<float4*>(dv.buf.obs_f32 + env * 8);
-      orow[0] = make_float4(t0, t1, t2, o0);
-      orow[1] = IS_IW ? make_float4(o1, o2, o3, o4) : make_float4(o1, o2, 0.f, 0.f);
-      snapshot_info = out_info & ~SHIPENV_INFO_DONE;
-    }
-    double* ef = dv.buf.env_f64;
-    ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
-    ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
-    ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
-    ef[SHIPENV_EF_N_BASE * B + env] = n_base;
-    ef[SHIPENV_EF_E_BASE * B + env] = e_base;
-    ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
-    ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
-    int* ei = dv.buf.env_i32;
-    ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
-    ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot_info;
-    ei[SHIPENV_EI_FLAGS * B + env] = flags;
-    if (G.collav == SHIPENV_COLLAV_SIMPLE) {
-      dv.buf.prev_f32[0 * B + env] = ps_tn; dv.buf.prev_f32[1 * B + env] = ps_te;
-      dv.buf.prev_f32[2 * B + env] = ps_on; dv.buf.prev_f32[3 * B + env] = ps_oe;
-    }
-    if (IS_RL && MODE == MODE_STEP && !write_snapshot_only) out_reward = acc_reward;
-    dv.buf.reward[env] = out_reward;
-    dv.buf.info_i32[env] = out_info;
-    dv.buf.nsub_i32[env] = nsub;
   }
 }
 
@@ -943,30 +995,53 @@ cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// persistent grid: as many CTAs as are resident at once (queried per instantiation), never more than
+// the environments need
+template <int MODEL, int ENVKIND, int MODE>
+static void launch_env_inst(const SenvView& v, const double* actions, int k, unsigned long long* queue,
+                            int sm_count, int persistent, cudaStream_t st) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE>, kBlock, 0) != cudaSuccess || n < 1)
+      n = SENV_MIN_BLOCKS;
+    per_sm = n;
+  }
+  const long long need = (2 * v.num_envs + kBlock - 1) / kBlock;
+  const long long resident = (long long)per_sm * (sm_count > 0 ? sm_count : 148);
+  // persistent: resident CTAs only, lane pairs refill from the queue; otherwise one slot per environment
+  const int grid = (int)((persistent && resident < need) ? resident : need);
+  k_env<MODEL, ENVKIND, MODE><<<grid, kBlock, 0, st>>>(v, actions, k, queue);
+}
+
 template <int MODEL, int MODE>
-static void launch_env_kind(const SenvView& v, int env_kind, const double* actions, int k, cudaStream_t st) {
-  const int grid = ship_grid(v);
+static void launch_env_kind(const SenvView& v, int env_kind, const double* actions, int k, unsigned long long* queue,
+                            int sm_count, int persistent, cudaStream_t st) {
   switch (env_kind) {
     case SHIPENV_ENV_COLAV_NONIW:
-      k_env<MODEL, SHIPENV_ENV_COLAV_NONIW, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      launch_env_inst<MODEL, SHIPENV_ENV_COLAV_NONIW, MODE>(v, actions, k, queue, sm_count, persistent, st);
       break;
     case SHIPENV_ENV_COLAV_IW:
-      k_env<MODEL, SHIPENV_ENV_COLAV_IW, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      launch_env_inst<MODEL, SHIPENV_ENV_COLAV_IW, MODE>(v, actions, k, queue, sm_count, persistent, st);
       break;
     default:
-      k_env<MODEL, SHIPENV_ENV_RL, MODE><<<grid, kBlock, 0, st>>>(v, actions, k);
+      launch_env_inst<MODEL, SHIPENV_ENV_RL, MODE>(v, actions, k, queue, sm_count, persistent, st);
       break;
   }
 }
 
 cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,
-                       cudaStream_t st) {
+                       unsigned long long* queue, int sm_count, int persistent, cudaStream_t st) {
+  // queue[0] = work-queue counter, queue[1] = environments found already done by this launch; both
+  // restart at 0 for every launch (ordered on the same stream)
+  cudaError_t e = cudaMemsetAsync(queue, 0, 2 * sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
   if (model == SHIPENV_MODEL_SIMPLE) {
-    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_STEP>(v, env_kind, actions, k, st);
-    else launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_SUBSTEPS>(v, env_kind, actions, k, st);
+    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
+    else launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
   } else {
-    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_STEP>(v, env_kind, actions, k, st);
-    else launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_SUBSTEPS>(v, env_kind, actions, k, st);
+    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
+    else launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
   }
   return cudaGetLastError();
 }
@@ -978,6 +1053,6 @@ cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st)
 }
 
 #else
-template __global__ void k_env<0, 1, 0>(DevView, const double*, int);
+template __global__ void k_env<0, 1, 0>(DevView, const double*, int, unsigned long long*);
 #endif
 }  // namespace SENV_NS

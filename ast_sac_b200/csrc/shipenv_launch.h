@@ -31,7 +31,7 @@ struct SenvView {
                            int reinit, cudaStream_t st);                                                       \
   cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st);                                            \
   cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,   \
-                         cudaStream_t st);                                                                     \
+                         unsigned long long* queue, int sm_count, int persistent, cudaStream_t st);            \
   cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st);                            \
   }
 
