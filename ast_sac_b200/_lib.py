@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 2
+ABI_VERSION = 3
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED = 0, 1
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2

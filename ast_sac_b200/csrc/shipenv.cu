@@ -49,6 +49,7 @@ struct shipenv {
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
   int sm_count = 0;
   unsigned* grid_dev = nullptr;       // culling grid cells
+  unsigned long long* edges_dev = nullptr;   // per-cell ring-segment masks
   SenvGrid grid{};
   // staging for the *_host entry points
   double* act_dev = nullptr;
@@ -172,6 +173,21 @@ int build_grid(shipenv* h) {
     ny = (int)std::ceil(ht / cell);
   }
   std::vector<unsigned> cells((size_t)nx * ny, 0u);
+  std::vector<unsigned long long> edges((size_t)nx * ny * 2, 0ull);
+  const int n_vert = p.n_poly > 0 ? p.poly_start[p.n_poly] : 0;
+  // segment i: vertex i -> next vertex of its polygon
+  std::vector<int> seg_next(n_vert, 0);
+  for (int q = 0; q < p.n_poly; ++q)
+    for (int i = p.poly_start[q]; i < p.poly_start[q + 1]; ++i)
+      seg_next[i] = (i + 1 < p.poly_start[q + 1]) ? i + 1 : p.poly_start[q];
+  auto seg_dist = [&](int i, double x, double y) {
+    const int k = seg_next[i];
+    const double ax = p.vert_e[i], ay = p.vert_n[i], dx = p.vert_e[k] - ax, dy = p.vert_n[k] - ay;
+    const double l2 = dx * dx + dy * dy;
+    double t = l2 > 0 ? ((x - ax) * dx + (y - ay) * dy) / l2 : 0.0;
+    t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    return std::hypot(x - (ax + t * dx), y - (ay + t * dy));
+  };
   const double half_len = 0.5 * std::fmax(p.ship[0].l_ship, p.ship[1].l_ship);
   const double halfdiag = cell * 0.70710678118654757 + 1e-6 * cell;
   const double r_contains = halfdiag + half_len * 1.4142135623730951 + 1.0;
@@ -186,11 +202,31 @@ int build_grid(shipenv* h) {
         if (d <= r_dist) m |= 1u << (16 + q);
       }
       cells[(size_t)iy * nx + ix] = m;
+      // ring segments that can be the nearest one to a point of the cell: the distance to a segment is
+      // convex, so its maximum over the cell is attained at a corner (upper bound U = min over segments of
+      // that maximum) and it is 1-Lipschitz (lower bound = distance at the centre - half diagonal)
+      const double x0 = p.map_min_e + ix * cell, x1 = x0 + cell, y0 = p.map_min_n + iy * cell, y1 = y0 + cell;
+      double U = INFINITY;
+      for (int i = 0; i < n_vert; ++i) {
+        const double mx = std::fmax(std::fmax(seg_dist(i, x0, y0), seg_dist(i, x1, y0)),
+                                    std::fmax(seg_dist(i, x0, y1), seg_dist(i, x1, y1)));
+        U = std::fmin(U, mx);
+      }
+      const double slack = 1e-6 * cell + 1e-3;
+      for (int i = 0; i < n_vert && i < 128; ++i) {
+        const double lo = seg_dist(i, cx, cy) - halfdiag;
+        if (lo <= U + slack && lo <= 1000.0 + slack)
+          edges[((size_t)iy * nx + ix) * 2 + (i >> 6)] |= 1ull << (i & 63);
+      }
     }
   if (h->grid_dev) cudaFree(h->grid_dev);
+  h->grid_dev = nullptr;
   CUDA_TRY(cudaMalloc(&h->grid_dev, cells.size() * sizeof(unsigned)));
   CUDA_TRY(cudaMemcpy(h->grid_dev, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-  h->grid = SenvGrid{h->grid_dev, p.map_min_e, p.map_min_n, 1.0 / cell, nx, ny};
+  if (h->edges_dev) cudaFree(h->edges_dev);
+  CUDA_TRY(cudaMalloc(&h->edges_dev, edges.size() * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemcpy(h->edges_dev, edges.data(), edges.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  h->grid = SenvGrid{h->grid_dev, h->edges_dev, p.map_min_e, p.map_min_n, 1.0 / cell, nx, ny};
   return SHIPENV_OK;
 }
 
@@ -308,6 +344,7 @@ int shipenv_destroy(shipenv_t* h) {
   }
   cudaFree(h->params_dev);
   cudaFree(h->grid_dev);
+  cudaFree(h->edges_dev);
   cudaFree(h->queue_dev);
   if (h->done_host) cudaFreeHost(h->done_host);
   cudaFree(h->act_dev);

@@ -179,6 +179,8 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     thrust = cmd;
   } else {
     const double w = s.omega;
+    // (the divisions stay exact in both builds: replacing them by reciprocal multiplications moved the
+    //  ill-conditioned detailed model past 1e-9 on one golden episode, rl_dt4_PTO)
     const double a_me = cmd * P.p_me / (w + 0.1);
     const double tq_me = (P.tq_me_max < a_me) ? P.tq_me_max : a_me;
     const double a_el = cmd * P.p_el / (w + 0.1);
@@ -264,6 +266,7 @@ struct MapView {
   const double* vn;
   const int* start;
   const double* bbox;   // [n_poly][4] = min_e, max_e, min_n, max_n (shared memory)
+  const unsigned char* next;   // [n_vert] index of the vertex that ends ring segment i (shared memory)
   int n_poly;
   MapGrid grid;
 };
@@ -307,20 +310,37 @@ __device__ __forceinline__ bool map_contains(const MapView& mp, unsigned mask, d
 }
 
 // PolygonObstacle.obstacles_distance (obstacle.py:138-141): min over polygons of the ring distance.
-// Only its value when <= 1000 m matters to the caller (reward_function.py:386-389, 454-457), so
-// polygons farther than that (not in `mask`) are skipped: they cannot hold the minimum if it is
-// <= 1000 m, and if it is not the reward term is 0 either way.
-__device__ __forceinline__ double map_distance(const MapView& mp, unsigned mask, double n_pos, double e_pos) {
+// Only its value when <= 1000 m matters to the caller (reward_function.py:386-389, 454-457).  The grid
+// cell lists the ring segments that can be nearest to a point of the cell within that clip (a segment
+// whose lower distance bound over the cell exceeds the smallest upper bound cannot be the nearest one),
+// so the minimum over the listed segments equals the minimum over all segments whenever it is <= 1000 m,
+// and when no segment is listed the reward term is 0 either way.
+__device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, double e_pos) {
   const double px = e_pos, py = n_pos;
+  unsigned long long m0, m1;
+  {
+    const double fx = (e_pos - mp.grid.e0) * mp.grid.inv_cell;
+    const double fy = (n_pos - mp.grid.n0) * mp.grid.inv_cell;
+    if (!(fx >= 0.0 && fy >= 0.0 && fx < (double)mp.grid.nx && fy < (double)mp.grid.ny)) {
+      // outside the grid (or NaN): every segment
+      const int nv = mp.start[mp.n_poly];
+      m0 = (nv >= 64) ? ~0ull : ((1ull << nv) - 1ull);
+      m1 = (nv > 64) ? ((nv >= 128) ? ~0ull : ((1ull << (nv - 64)) - 1ull)) : 0ull;
+    } else {
+      const ulonglong2 mm = __ldg(reinterpret_cast<const ulonglong2*>(mp.grid.edges) + ((int)fy * mp.grid.nx + (int)fx));
+      m0 = mm.x; m1 = mm.y;
+    }
+  }
   double best2 = INFINITY;
-  while (mask) {
-    const int p = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int a = mp.start[p], b = mp.start[p + 1];
-    double ax = mp.ve[b - 1], ay = mp.vn[b - 1];
-    for (int i = a; i < b; ++i) {
-      // ring segment (i-1) -> i; the reference walks i -> i+1, same set of segments
-      const double bx = mp.ve[i], by = mp.vn[i];
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    unsigned long long m = half ? m1 : m0;
+    while (m) {
+      const int i = __ffsll((long long)m) - 1 + 64 * half;
+      m &= m - 1;
+      // segment i -> next vertex of the same polygon (mp.next[i])
+      const int k = mp.next[i];
+      const double ax = mp.ve[i], ay = mp.vn[i], bx = mp.ve[k], by = mp.vn[k];
       const double dx = bx - ax, dy = by - ay;
       const double l2 = dx * dx + dy * dy;
       double t = 0.0;
@@ -332,7 +352,6 @@ __device__ __forceinline__ double map_distance(const MapView& mp, unsigned mask,
       const double cx = ax + t * dx, cy = ay + t * dy;
       const double d2 = (px - cx) * (px - cx) + (py - cy) * (py - cy);
       best2 = (d2 < best2) ? d2 : best2;
-      ax = bx; ay = by;
     }
   }
   return sqrt(best2);   // sqrt is monotonic and correctly rounded: sqrt(min d2) == min sqrt(d2)
@@ -387,6 +406,7 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
 struct SharedBlock {
   ShipEnvParams p;
   double bbox[SHIPENV_MAX_POLY * 4];
+  unsigned char next[SHIPENV_MAX_VERT];
 };
 
 __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
@@ -402,6 +422,8 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
       mnn = fmin(mnn, sb.p.vert_n[i]); mxn = fmax(mxn, sb.p.vert_n[i]);
     }
     sb.bbox[4 * p + 0] = mne; sb.bbox[4 * p + 1] = mxe; sb.bbox[4 * p + 2] = mnn; sb.bbox[4 * p + 3] = mxn;
+    for (int i = sb.p.poly_start[p]; i < sb.p.poly_start[p + 1]; ++i)
+      sb.next[i] = (unsigned char)((i + 1 < sb.p.poly_start[p + 1]) ? i + 1 : sb.p.poly_start[p]);
   }
   __syncthreads();
 }
@@ -569,7 +591,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
   const bool dynamic_route = IS_IW && role == 1;
-  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, G.n_poly, dv.grid};
+  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
   const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
   const bool collav_lane = (G.collav == SHIPENV_COLLAV_SIMPLE) && (role == 0 || !IS_IW);
   const double collav_bias = IS_RL ? (-15.0 * (kPi / 180.0)) : (15.0 * (kPi / 180.0));
@@ -752,7 +774,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
       if (IS_RL) {
-        const double gd = map_distance(mp, cell >> 16, s.north, s.east);
+        const double gd = map_distance(mp, s.north, s.east);
         const double aect = fabs(s.e_ct);
         if (role == 0) {
           // test_ship_grounding_reward / test_ship_nav_failure_reward (reward_function.py:359-425)

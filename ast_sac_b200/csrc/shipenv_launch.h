@@ -14,6 +14,10 @@
 // tests give the same answers as testing every polygon.
 struct SenvGrid {
   const unsigned* cells;
+  // per cell, 128-bit mask over the map's ring segments (segment i runs from vertex i to the next vertex
+  // of its polygon): the segments that can be the nearest one, within the 1000 m clip, to some point of
+  // the cell.  edges[2*c] = segments 0..63, edges[2*c+1] = segments 64..127.
+  const unsigned long long* edges;
   double e0, n0, inv_cell;
   int nx, ny;
 };
