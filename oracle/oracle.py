@@ -18,7 +18,7 @@ MAX_WP, MAX_POLY, MAX_VERT = 32, 16, 128
 MODEL_SIMPLE, MODEL_DETAILED = 0, 1
 HSG = {"MOTOR": 0, "GEN": 1, "OFF": 2}
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
-COLLAV = {"none": 0, None: 0, "simple": 1}
+COLLAV = {"none": 0, None: 0, "simple": 1, "sbmpc": 2}
 
 EVENT_STRINGS = [  # get_env_info.py:143-202 / reward_function.py:204-262, env.py:684
     'Ships collision!',
@@ -102,7 +102,8 @@ class EnvState(C.Structure):
         ("states", C.c_float * 8), ("next_observations", C.c_float * 8), ("initial_states", C.c_float * 8),
         ("snapshot_events", C.c_int32), ("snapshot_terminal", C.c_int32), ("snapshot_test_stop", C.c_int32),
         ("snapshot_obs_stop", C.c_int32), ("sampling_count", C.c_int32), ("tracker_active", C.c_int32),
-        ("n_substeps", C.c_int64)]
+        ("n_substeps", C.c_int64), ("sb_p_last", _D), ("sb_chi_last", _D), ("sb_active", C.c_int32),
+        ("pad2_", C.c_int32)]
 
 
 class StepResult(C.Structure):

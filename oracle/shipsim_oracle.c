@@ -91,6 +91,9 @@ void orc_ship_init(const OrcShipConfig* c, OrcShipState* s) {
 /* ---------------------------------------------------------------------------------------------
  * NavigationSystem.next_wpt + los_guidance, LOS_guidance.py:83-117
  * ------------------------------------------------------------------------------------------- */
+/* NavigationSystem.los_guidance(k, N, E), LOS_guidance.py:100-117 */
+static double los_guidance(const OrcShipConfig* c, OrcShipState* s, int k);
+
 static double los_heading_ref(const OrcShipConfig* c, OrcShipState* s) {
   int k = s->next_wpt;
   double N = s->north, E = s->east;
@@ -99,7 +102,11 @@ static double los_heading_ref(const OrcShipConfig* c, OrcShipState* s) {
     if (s->n_wp > k + 1) { s->next_wpt = k + 1; s->prev_wpt = k; }
     else { s->next_wpt = k; s->prev_wpt = k; }
   } else { s->next_wpt = k; s->prev_wpt = k - 1; }
-  k = s->next_wpt;
+  return los_guidance(c, s, s->next_wpt);
+}
+
+static double los_guidance(const OrcShipConfig* c, OrcShipState* s, int k) {
+  double N = s->north, E = s->east;
   double dx = s->wp_north[k] - s->wp_north[k - 1];
   double dy = s->wp_east[k] - s->wp_east[k - 1];
   double alpha_k = atan2(dy, dx);
@@ -480,6 +487,7 @@ void orc_env_construct(const OrcEnvConfig* cfg, OrcEnvState* st) {
   memcpy(st->states, st->initial_states, sizeof(st->states));
   init_iw(cfg, st);
   snapshot_init(st);
+  st->sb_p_last = 1.0; st->sb_chi_last = 0.0; st->sb_active = 0;   /* SBMPCParams defaults */
 }
 
 void orc_env_init_step(const OrcEnvConfig* cfg, OrcEnvState* st) {   /* :1053-1097 / :297-342 */
@@ -517,6 +525,106 @@ static int collision_risk_f32(const OrcEnvState* st) {
   return d2 < 9000000.0f;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * SBMPC collision avoidance: sbmpc.py:90-314, sbmpc_misc.py:3-123, as the env calls it
+ * (rl_env env.py:360-385, run_colav env.py:1145-1170) with SBMPC(tf=1000, dt=20) and default SBMPCParams
+ * (KAPPA_ = 0, so the COLREGs term mu never contributes and is not restated).
+ * ------------------------------------------------------------------------------------------- */
+#define SB_NSAMP 50                      /* int(T / DT) = int(1000 / 20) */
+#define SB_DT 20.0
+
+static double wrap_pmpi(double a) {      /* wrap_angle_to_pmpi, sbmpc_misc.py:3-33 */
+  return -ORC_PI + py_mod(a - (-ORC_PI), ORC_PI - (-ORC_PI));
+}
+
+static void sbmpc_offsets(const OrcEnvConfig* cfg, OrcEnvState* st, double u_d, double chi_d,
+                          double* speed_factor, double* heading_offset) {
+  const OrcShipState* os = &st->ship[0];
+  const OrcShipState* ob = &st->ship[1];
+  /* os_state = [east, north, -yaw, u, v, r]; obstacle state = [east, north, -yaw, u, v] */
+  const double os_x = os->east, os_y = os->north, os_v = os->v;
+  const double obs_l = cfg->ship[1].length_of_ship, obs_w = cfg->ship[1].width_of_ship;
+  const double os_l = 25.0, os_w = 80.0;                   /* ShipLinearModel defaults, sbmpc_misc.py:86 */
+  (void)os_w;
+  /* Obstacle.__init__ + calculate_trajectory, sbmpc_misc.py:34-83 */
+  double ox[SB_NSAMP], oy[SB_NSAMP];
+  const double opsi = -ob->yaw, ou = ob->u, ov = ob->v;
+  const double o11 = -sin(opsi), o12 = cos(opsi), o21 = cos(opsi), o22 = sin(opsi);
+  ox[0] = ob->east; oy[0] = ob->north;
+  for (int i = 1; i < SB_NSAMP; ++i) {
+    ox[i] = ox[i - 1] + (o11 * ou + o12 * ov) * SB_DT;
+    oy[i] = oy[i - 1] + (o21 * ou + o22 * ov) * SB_DT;
+  }
+  /* activation, sbmpc.py:154-166 */
+  const double d0 = ox[0] - os_x, d1 = oy[0] - os_y;
+  st->sb_active = sqrt(d0 * d0 + d1 * d1) < 2000.0;
+  if (!st->sb_active) {
+    st->sb_p_last = 1; st->sb_chi_last = 0;
+    *speed_factor = 1; *heading_offset = 0;
+    return;
+  }
+  static const double chi_deg[7] = {-30.0, -20.0, -10.0, 0.0, 10.0, 20.0, 30.0};
+  static const double p_ca[4] = {0.4, 0.6, 0.8, 1.0};
+  const double PHI = 68.5 * (ORC_PI / 180.0);               /* PHI_AH_ = PHI_OT_ */
+  const double cos_ot = cos(PHI * (ORC_PI / 180.0));        /* np.cos(np.deg2rad(PHI_OT_)): degrees twice */
+  const double d_safe = 1000.0, d_close = 2000.0;
+  /* obstacle velocity in the world frame: rot2d(obstacle.psi_, [u, v]), sbmpc.py:312-314 */
+  const double vo0 = -sin(opsi) * ou + cos(opsi) * ov, vo1 = cos(opsi) * ou + sin(opsi) * ov;
+  const double n_vo = sqrt(vo0 * vo0 + vo1 * vo1);
+  double cost = INFINITY, u_best = 1, chi_best = 0;
+  for (int ic = 0; ic < 7; ++ic) {
+    const double chi_ca = chi_deg[ic] * (ORC_PI / 180.0);   /* np.deg2rad */
+    for (int jp = 0; jp < 4; ++jp) {
+      /* ShipLinearModel.linear_pred(os_state, u_d * P, chi_d + Chi), sbmpc_misc.py:102-122 */
+      const double ud = u_d * p_ca[jp], psi_d = chi_d + chi_ca;
+      const double psi0 = wrap_pmpi(psi_d);
+      const double r11 = -sin(psi_d), r12 = cos(psi_d), r21 = cos(psi_d), r22 = sin(psi_d);
+      double sx = os_x, sy = os_y, su = ud, sv = os_v;
+      double H1 = 0, t = 0;
+      for (int i = 0; i < SB_NSAMP; ++i) {
+        if (i > 0) {
+          sx = sx + SB_DT * (r11 * su + r12 * sv);
+          sy = sy + SB_DT * (r21 * su + r22 * sv);
+          su = ud; sv = 0;
+        }
+        const double spsi = (i == 0) ? psi0 : psi_d;
+        t += SB_DT;
+        const double e0 = ox[i] - sx, e1 = oy[i] - sy;
+        const double dist = sqrt(e0 * e0 + e1 * e1);
+        double R = 0, Cc = 0;
+        if (dist < d_close) {
+          const double vs0 = -sin(spsi) * su + cos(spsi) * sv, vs1 = cos(spsi) * su + sin(spsi) * sv;
+          double d_safe_i;
+          const double phi_o = wrap_pmpi(atan2(-e1, -e0) - opsi + ORC_PI / 2);
+          if (phi_o < PHI) d_safe_i = d_safe + obs_l / 2;
+          else if (phi_o > PHI) d_safe_i = 0.5 * d_safe + obs_l / 2;
+          else d_safe_i = d_safe + obs_w / 2;
+          const double n_vs = sqrt(vs0 * vs0 + vs1 * vs1);
+          const double dot = vs0 * vo0 + vs1 * vo1;
+          if (dot > cos_ot * n_vs * n_vo && n_vs > n_vo) d_safe_i = d_safe + os_l / 2 + obs_l / 2;
+          if (dist < d_safe_i) {
+            R = (1 / pow(fabs(t - 0), 1.0)) * pow(d_safe / dist, 4.0);
+            const double k_coll = 1e-6 * os_l * obs_l;
+            const double w0 = vs0 - vo0, w1 = vs1 - vo1;
+            Cc = k_coll * pow(sqrt(w0 * w0 + w1 * w1), 2.0);
+          }
+        }
+        const double H0 = Cc * R + 0.0;                      /* + KAPPA_ * mu with KAPPA_ = 0 */
+        if (H0 > H1) H1 = H0;
+      }
+      const double d_chi = chi_ca - st->sb_chi_last;         /* delta_Chi, sbmpc.py:303-310 */
+      double dl_chi = 0;
+      if (d_chi > 0) dl_chi = 20 * (d_chi * d_chi);
+      else if (d_chi < 0) dl_chi = 30 * (d_chi * d_chi);
+      const double H2 = 25 * (1 - p_ca[jp]) + 30 * (chi_ca * chi_ca) + 20 * fabs(st->sb_p_last - p_ca[jp]) + dl_chi;
+      const double cost_i = H1 + H2;                         /* single obstacle: max over k */
+      if (cost_i < cost) { cost = cost_i; u_best = p_ca[jp]; chi_best = chi_ca; }
+    }
+  }
+  st->sb_p_last = u_best; st->sb_chi_last = chi_best;
+  *speed_factor = u_best; *heading_offset = chi_best;
+}
+
 /* one asset's part of _step(): test_step / obs_step.  out5 = the returned next_states array
  * (3 entries in the normal branch of test_step / NonIW obs_step, 5 otherwise). */
 static int asset_step(const OrcEnvConfig* cfg, OrcEnvState* st, int who, float* out5) {
@@ -535,8 +643,15 @@ static int asset_step(const OrcEnvConfig* cfg, OrcEnvState* st, int who, float* 
   }
   double forward_speed = s->u;
   int collav_here = (who == 0) || (cfg->env_kind == ORC_ENV_COLAV_NONIW);
-  double rudder = autopilot_rudder(c, s, -0.0);
-  double cmd = speed_command(c, s, c->desired_forward_speed * 1.0);
+  double speed_factor = 1.0, heading_offset = 0.0;
+  if (collav_here && cfg->collav == ORC_COLLAV_SBMPC) {
+    /* rl_env env.py:360-385: next_wpt's result is discarded, los_guidance runs on the OLD waypoint
+     * index and advances the LOS integrator a first time (quirk 2 of SURVEY.md section 8) */
+    double chi_d = los_guidance(c, s, s->next_wpt);
+    sbmpc_offsets(cfg, st, c->desired_forward_speed, -chi_d, &speed_factor, &heading_offset);
+  }
+  double rudder = autopilot_rudder(c, s, -heading_offset);
+  double cmd = speed_command(c, s, c->desired_forward_speed * speed_factor);
   if (collav_here && cfg->collav == ORC_COLLAV_SIMPLE && collision_risk_f32(st)) {
     cmd *= 0.5;
     cmd = (cmd < 0.0) ? 0.0 : ((cmd > 1.1) ? 1.1 : cmd);         /* np.clip(x, 0.0, 1.1) */

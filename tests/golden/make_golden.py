@@ -242,6 +242,20 @@ def main():
     save("rl_dt4_PTO", iw_episode("rl", 4, kat_actions, mode="PTO"))
     save("rl_dt4_MEC", iw_episode("rl", 4, kat_actions, mode="MEC"))
 
+    # --- SBMPC collision avoidance (the trainer's default collav mode) ---
+    save("rl_dt4_sbmpc_kat", iw_episode("rl", 4, kat_actions, collav="sbmpc"))
+    save("colav_iw_dt4_sbmpc_kat", iw_episode("colav", 4, kat_actions, collav="sbmpc"))
+    # small scoping angles: the ships meet head-on on the shared track, SBMPC active for a long stretch
+    save("rl_dt4_sbmpc_encounter", iw_episode("rl", 4, np.array(
+        [-0.04947389, 0.02654783, 0.00399436, -0.01783045, 0.03020418, -0.02060939, -0.00486969, -0.03832306,
+         -0.01014598]), collav="sbmpc"))
+    save("colav_iw_dt4_sbmpc_encounter", iw_episode("colav", 4, np.array(
+        [0.02003677, -0.03365987, -0.01086403, -0.05174993, -0.0248715, -0.00825309, -0.04126783, 0.01394448,
+         -0.01252194]), collav="sbmpc"))
+    save("rl_dt4_sbmpc_rand0", iw_episode("rl", 4, np.random.default_rng(777).uniform(-np.pi / 6, np.pi / 6, size=9) * 0.3,
+                                          collav="sbmpc"))
+    save("colav_noniw_dt4_sbmpc", noniw_run(4, collav="sbmpc"))
+
     # --- NonIW env (config 1) ---
     save("colav_noniw_dt4", noniw_run(4))
     save("colav_noniw_dt30", noniw_run(30))
