@@ -13,11 +13,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED = 0, 1
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
-COLLAV_NONE, COLLAV_SIMPLE = 0, 1
+COLLAV_NONE, COLLAV_SIMPLE, COLLAV_SBMPC = 0, 1, 2
 
 INFO_EVENT_MASK = 0x7ff
 INFO_TERMINAL, INFO_TEST_STOP, INFO_OBS_STOP, INFO_DONE, INFO_UNBOUND = 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20
@@ -25,8 +25,9 @@ INFO_TERMINAL, INFO_TEST_STOP, INFO_OBS_STOP, INFO_DONE, INFO_UNBOUND = 1 << 16,
 SF = dict(north=0, east=1, yaw=2, u=3, v=4, r=5, omega=6, time=7, e_ct=8, e_ct_int=9, hdg_err_i=10,
           hdg_prev_err=11, spd_err_i=12, spd_aux=13)
 SF_COUNT = 14
-EF = dict(travel_dist=0, travel_time=1, acc_reward=2, n_base=3, e_base=4, log_north=5, log_east=6)
-EF_COUNT = 7
+EF = dict(travel_dist=0, travel_time=1, acc_reward=2, n_base=3, e_base=4, log_north=5, log_east=6, sb_p_last=7,
+          sb_chi_last=8)
+EF_COUNT = 9
 EI = dict(sampling_count=0, snapshot_info=1, flags=2)
 EI_COUNT = 3
 
@@ -46,8 +47,8 @@ SHIP_PARAM_DOUBLES = [
 
 class ShipParams(C.Structure):
     _fields_ = [(n, _D) for n in SHIP_PARAM_DOUBLES] + [
-        ("wp_north", _D * MAX_WP), ("wp_east", _D * MAX_WP),
-        ("n_wp", C.c_int32), ("model_kind", C.c_int32), ("pad_", C.c_int32 * 2)]
+        ("wp_north", _D * MAX_WP), ("wp_east", _D * MAX_WP), ("w_ship", _D),
+        ("n_wp", C.c_int32), ("model_kind", C.c_int32)]
 
 
 class Params(C.Structure):

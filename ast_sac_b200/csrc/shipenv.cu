@@ -67,8 +67,8 @@ int validate(const ShipEnvParams* p, long long num_envs) {
     return fail(SHIPENV_E_ARG, "params.abi_version %d != %d", p->abi_version, SHIPENV_ABI_VERSION);
   if (num_envs <= 0) return fail(SHIPENV_E_ARG, "num_envs must be positive");
   if (p->env_kind < SHIPENV_ENV_COLAV_NONIW || p->env_kind > SHIPENV_ENV_RL) return fail(SHIPENV_E_ARG, "bad env_kind");
-  if (p->collav != SHIPENV_COLLAV_NONE && p->collav != SHIPENV_COLLAV_SIMPLE)
-    return fail(SHIPENV_E_ARG, "collav mode %d not supported (none=0, simple=1)", p->collav);
+  if (p->collav != SHIPENV_COLLAV_NONE && p->collav != SHIPENV_COLLAV_SIMPLE && p->collav != SHIPENV_COLLAV_SBMPC)
+    return fail(SHIPENV_E_ARG, "collav mode %d not supported (none=0, simple=1, sbmpc=2)", p->collav);
   if (p->max_sampling_frequency < 0 || p->max_sampling_frequency > SHIPENV_MAX_IW)
     return fail(SHIPENV_E_ARG, "max_sampling_frequency must be in [0, %d]", SHIPENV_MAX_IW);
   if (p->n_poly < 0 || p->n_poly > SHIPENV_MAX_POLY) return fail(SHIPENV_E_ARG, "n_poly out of range");
@@ -94,7 +94,9 @@ int validate(const ShipEnvParams* p, long long num_envs) {
   return SHIPENV_OK;
 }
 
-SenvView view(const shipenv* h) { return SenvView{h->params_dev, h->buf, h->num_envs, h->grid}; }
+SenvView view(const shipenv* h) {
+  return SenvView{h->params_dev, h->buf, h->num_envs, h->grid, h->params.collav == SHIPENV_COLLAV_SBMPC ? 1 : 0};
+}
 
 int check_ready(const shipenv* h, bool need_constructed) {
   if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");

@@ -99,17 +99,9 @@ __device__ __forceinline__ double sat(double val, double low, double hi) {   // 
 // 834-901, ship_engine.py:403-443, controllers.py:106-125,183-189,286-295,425-433,
 // LOS_guidance.py:83-117, utils.py:42-53.
 // ------------------------------------------------------------------------------------------------
-template <int MODEL>
-__device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
-                                          bool collav_hit, double collav_bias) {
-  // --- NavigationSystem.next_wpt
-  {
-    const double dn = s.wn - s.north, de = s.we - s.east;
-    if (dn * dn + de * de <= P.los_ra * P.los_ra) {
-      if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
-    }
-  }
-  // --- NavigationSystem.los_guidance
+// NavigationSystem.los_guidance on the cached segment wp[k-1] -> wp[k] (LOS_guidance.py:100-117): updates
+// e_ct and the LOS integrator, returns the heading reference.
+__device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship& s) {
   double e_ct = -(s.north - s.pn) * s.sin_a + (s.east - s.pe) * s.cos_a;
   const double R = P.los_r;
   if (e_ct * e_ct >= R * R) e_ct = 0.99 * R;
@@ -119,11 +111,28 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double q = e_ct / delta;
   if (fabs(s.e_ct_int + q) <= P.los_limit) s.e_ct_int += q;
   const double chi_r = atan(-q - s.e_ct_int * P.los_ki);
-  const double heading_ref = s.alpha + chi_r;
+  return s.alpha + chi_r;
+}
+
+// heading_offset / speed_factor: SBMPC's course offset (already negated, "pos == clockwise in sim",
+// env.py:394) and speed factor; (-0.0, 1.0) without SBMPC.
+template <int MODEL>
+__device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
+                                          bool collav_hit, double collav_bias, double heading_offset,
+                                          double speed_factor) {
+  // --- NavigationSystem.next_wpt
+  {
+    const double dn = s.wn - s.north, de = s.we - s.east;
+    if (dn * dn + de * de <= P.los_ra * P.los_ra) {
+      if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
+    }
+  }
+  // --- NavigationSystem.los_guidance
+  const double heading_ref = los_guidance(P, s);
   // --- heading PID -> rudder angle
   double rudder;
   {
-    const double error = (heading_ref + (-0.0)) - s.yaw;
+    const double error = (heading_ref + heading_offset) - s.yaw;
 #if SENV_FAST_MATH
     const double d_error = (error - s.hdg_prev_err) * P.inv_ctrl_dt;
 #else
@@ -137,8 +146,9 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   }
   // --- speed controller
   double cmd;
+  const double speed_set_point = P.desired_speed * speed_factor;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
-    const double error = P.desired_speed - s.u;
+    const double error = speed_set_point - s.u;
 #if SENV_FAST_MATH
     const double d_error = (error - s.spd_aux) * P.inv_ctrl_dt;
 #else
@@ -150,7 +160,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     const double out = error * P.spd_kp + d_error * P.spd_kd + error_i * P.spd_ki;
     cmd = sat(out, -P.max_thrust, P.max_thrust);
   } else {
-    const double error = P.desired_speed - s.u;
+    const double error = speed_set_point - s.u;
     const double error_i = s.spd_err_i + error * P.ctrl_dt;
     s.spd_err_i = error_i;
     const double w_d = sat(error * P.kp_ship_speed + error_i * P.ki_ship_speed, 0.0, P.max_shaft_speed);
@@ -402,6 +412,137 @@ __device__ __forceinline__ double shfl_xor_f64(double v, int lane_mask) {
   return __shfl_xor_sync(FULL_MASK, v, lane_mask);
 }
 
+// ------------------------------------------------------------------------------------------------
+// SBMPC collision avoidance (sbmpc.py:90-314, sbmpc_misc.py:3-123) as the envs call it: SBMPC(tf=1000,
+// dt=20) with the default SBMPCParams, one dynamic obstacle.  7 course offsets x 4 speed factors = 28
+// control behaviours, each a 50-sample straight-line prediction of both ships; cost = max over the
+// samples of collision cost x risk, plus the manoeuvring penalties.  KAPPA_ = 0, so the COLREGs term mu
+// never contributes and is not evaluated.
+//
+// One warp evaluates one environment: lane b < 28 takes behaviour (Chi_ca_[b / 4], P_ca_[b % 4]), the
+// reference's loop order, and the first minimum in that order wins (strict `<` in sbmpc.py:176).
+// ------------------------------------------------------------------------------------------------
+constexpr int kSbSamples = 50;            // int(T_ / DT_) = int(1000 / 20)
+constexpr double kSbDt = 20.0;
+constexpr int kSbBehaviours = 28;
+
+struct SbmpcIn {
+  double os_x, os_y, os_v;                // own ship (ship under test): east, north, sway speed
+  double ob_x, ob_y, ob_psi, ob_u, ob_v;  // obstacle ship: east, north, -yaw, surge, sway
+  double u_d, chi_d;                      // nominal speed / course references of the calling ship
+  double chi_last, p_last;                // SBMPCParams.Chi_ca_last_, P_ca_last_
+};
+
+__device__ __forceinline__ double wrap_pmpi(double a) {     // wrap_angle_to_pmpi, sbmpc_misc.py:3-33
+  return -kPi + py_mod(a - (-kPi), kPi - (-kPi));
+}
+
+// cost of behaviour b (SBMPC.cost_func, sbmpc.py:190-296, for the prediction of linear_pred,
+// sbmpc_misc.py:102-122, against Obstacle.calculate_trajectory, sbmpc_misc.py:58-83)
+__device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, double obs_l, double obs_w) {
+  const int ic = b >> 2, jp = b & 3;
+  const double chi_ca = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);       // np.deg2rad(Chi_ca_[ic])
+  const double p_ca = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
+  const double os_l = 25.0;                                 // ShipLinearModel defaults, sbmpc_misc.py:86
+  const double d_safe = 1000.0, d_close = 2000.0;
+  const double PHI = 1.1955505376161157;                    // PHI_AH_ = PHI_OT_ = np.deg2rad(68.5)
+  const double cos_ot = 0.9997823068017366;                 // np.cos(np.deg2rad(PHI_OT_)): degrees applied twice
+  // obstacle: constant velocity along its heading
+  double so, co;
+  sincos(in.ob_psi, &so, &co);
+  const double ob_dx = ((-so) * in.ob_u + co * in.ob_v) * kSbDt;
+  const double ob_dy = (co * in.ob_u + so * in.ob_v) * kSbDt;
+  const double vo0 = (-so) * in.ob_u + co * in.ob_v, vo1 = co * in.ob_u + so * in.ob_v;   // rot2d, sbmpc.py:312-314
+  const double n_vo = sqrt(vo0 * vo0 + vo1 * vo1);
+  // own ship: heading psi_d from sample 1 on, wrapped heading and the measured sway speed at sample 0
+  const double ud = in.u_d * p_ca, psi_d = in.chi_d + chi_ca;
+  const double psi0 = wrap_pmpi(psi_d);
+  double s0, c0, sd, cd;
+  sincos(psi0, &s0, &c0);
+  sincos(psi_d, &sd, &cd);
+  const double zero = 0.0;
+  const double os_dx1 = kSbDt * ((-sd) * ud + cd * in.os_v), os_dy1 = kSbDt * (cd * ud + sd * in.os_v);   // 0 -> 1
+  const double os_dx = kSbDt * ((-sd) * ud + cd * zero), os_dy = kSbDt * (cd * ud + sd * zero);           // i -> i+1
+  // world-frame velocities and what depends only on them: sample 0 (A) and samples >= 1 (B)
+  const double vsA0 = (-s0) * ud + c0 * in.os_v, vsA1 = c0 * ud + s0 * in.os_v;
+  const double vsB0 = (-sd) * ud + cd * zero, vsB1 = cd * ud + sd * zero;
+  const double n_vsA = sqrt(vsA0 * vsA0 + vsA1 * vsA1), n_vsB = sqrt(vsB0 * vsB0 + vsB1 * vsB1);
+  const bool otA = (vsA0 * vo0 + vsA1 * vo1) > cos_ot * n_vsA * n_vo && n_vsA > n_vo;
+  const bool otB = (vsB0 * vo0 + vsB1 * vo1) > cos_ot * n_vsB * n_vo && n_vsB > n_vo;
+  const double k_coll = 1e-6 * os_l * obs_l;
+  const double nrA = sqrt((vsA0 - vo0) * (vsA0 - vo0) + (vsA1 - vo1) * (vsA1 - vo1));
+  const double nrB = sqrt((vsB0 - vo0) * (vsB0 - vo0) + (vsB1 - vo1) * (vsB1 - vo1));
+  const double ccA = k_coll * (nrA * nrA), ccB = k_coll * (nrB * nrB);   // K_COLL * |v_s - v_o| ** 2
+  // safety distance by the sector the own ship is seen in from the obstacle (sbmpc.py:232-245)
+  const double ds_ahead = d_safe + obs_l / 2, ds_behind = 0.5 * d_safe + obs_l / 2, ds_beam = d_safe + obs_w / 2;
+  const double ds_ot = d_safe + os_l / 2 + obs_l / 2;
+  const double ds_min = fmin(ds_ahead, fmin(ds_behind, ds_beam)), ds_max = fmax(ds_ahead, fmax(ds_behind, ds_beam));
+
+  double sx = in.os_x, sy = in.os_y, ox = in.ob_x, oy = in.ob_y;
+  double H1 = 0.0, t = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < kSbSamples; ++i) {
+    if (i > 0) {
+      sx = sx + ((i == 1) ? os_dx1 : os_dx);
+      sy = sy + ((i == 1) ? os_dy1 : os_dy);
+      ox = ox + ob_dx;
+      oy = oy + ob_dy;
+    }
+    t += kSbDt;
+    const double e0 = ox - sx, e1 = oy - sy;
+    const double d2 = e0 * e0 + e1 * e1;
+    if (!(d2 < 4.1e6)) continue;            // certainly dist >= D_CLOSE_: R = C = 0, H0 = 0 cannot raise H1
+    const double dist = sqrt(d2);
+    if (!(dist < d_close)) continue;
+    const bool ot = (i == 0) ? otA : otB;
+    bool within;
+    if (ot) within = dist < ds_ot;
+    else if (dist < ds_min) within = true;  // inside every sector's safety distance
+    else if (!(dist < ds_max)) within = false;
+    else {
+      const double phi_o = wrap_pmpi(atan2(-e1, -e0) - in.ob_psi + kPi / 2);
+      const double d_safe_i = (phi_o < PHI) ? ds_ahead : ((phi_o > PHI) ? ds_behind : ds_beam);
+      within = dist < d_safe_i;
+    }
+    if (within) {
+      const double q = d_safe / dist;
+      const double R = (1.0 / t) * ((q * q) * (q * q));     // (1 / |t - t0| ** P_) * (d_safe / dist) ** Q_
+      const double H0 = ((i == 0) ? ccA : ccB) * R + 0.0;   // + KAPPA_ * mu, KAPPA_ = 0
+      if (H0 > H1) H1 = H0;
+    }
+  }
+  const double d_chi = chi_ca - in.chi_last;                // delta_Chi, sbmpc.py:303-310
+  double dl_chi = 0.0;
+  if (d_chi > 0) dl_chi = 20.0 * (d_chi * d_chi);
+  else if (d_chi < 0) dl_chi = 30.0 * (d_chi * d_chi);
+  const double H2 = 25.0 * (1 - p_ca) + 30.0 * (chi_ca * chi_ca) + 20.0 * fabs(in.p_last - p_ca) + dl_chi;
+  return H1 + H2;
+}
+
+// get_optimal_ctrl_offset (sbmpc.py:113-185) for the environment whose inputs lane `src` holds: all 32
+// lanes take part, every lane returns the winning behaviour index (-1: no finite cost, keep (1, 0)).
+__device__ __forceinline__ int sbmpc_warp_argmin(const SbmpcIn& mine, int src, int lane, double obs_l, double obs_w) {
+  SbmpcIn in;
+  in.os_x = __shfl_sync(FULL_MASK, mine.os_x, src); in.os_y = __shfl_sync(FULL_MASK, mine.os_y, src);
+  in.os_v = __shfl_sync(FULL_MASK, mine.os_v, src);
+  in.ob_x = __shfl_sync(FULL_MASK, mine.ob_x, src); in.ob_y = __shfl_sync(FULL_MASK, mine.ob_y, src);
+  in.ob_psi = __shfl_sync(FULL_MASK, mine.ob_psi, src);
+  in.ob_u = __shfl_sync(FULL_MASK, mine.ob_u, src); in.ob_v = __shfl_sync(FULL_MASK, mine.ob_v, src);
+  in.u_d = __shfl_sync(FULL_MASK, mine.u_d, src); in.chi_d = __shfl_sync(FULL_MASK, mine.chi_d, src);
+  in.chi_last = __shfl_sync(FULL_MASK, mine.chi_last, src); in.p_last = __shfl_sync(FULL_MASK, mine.p_last, src);
+  double cost = INFINITY;
+  if (lane < kSbBehaviours) cost = sbmpc_behaviour_cost(in, lane, obs_l, obs_w);
+  if (!(cost < INFINITY)) cost = INFINITY;      // NaN / inf never win the reference's `cost_i < cost`
+  int idx = lane;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double oc = __shfl_xor_sync(FULL_MASK, cost, off);
+    const int oi = __shfl_xor_sync(FULL_MASK, idx, off);
+    if (oc < cost || (oc == cost && oi < idx)) { cost = oc; idx = oi; }
+  }
+  return (cost < INFINITY) ? idx : -1;
+}
+
 // shared-memory staging of the parameter block
 struct SharedBlock {
   ShipEnvParams p;
@@ -527,6 +668,11 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
       ef[SHIPENV_EF_E_BASE * dv.num_envs + env] = sb.p.e_base0;
       ef[SHIPENV_EF_LOG_NORTH * dv.num_envs + env] = s.north;
       ef[SHIPENV_EF_LOG_EAST * dv.num_envs + env] = s.east;
+      if (!do_init_step) {
+        // Env.__init__ creates the SBMPC object (env.py:123); reset() never touches its memory
+        ef[SHIPENV_EF_SB_P_LAST * dv.num_envs + env] = 1.0;
+        ef[SHIPENV_EF_SB_CHI_LAST * dv.num_envs + env] = 0.0;
+      }
       int* ei = dv.buf.env_i32;
       ei[SHIPENV_EI_SAMPLING_COUNT * dv.num_envs + env] = 0;
       ei[SHIPENV_EI_SNAPSHOT_INFO * dv.num_envs + env] = 0;
@@ -547,7 +693,7 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
       dv.buf.env_f64[SHIPENV_EF_LOG_EAST * dv.num_envs + env] = s.east;
       dv.buf.env_i32[SHIPENV_EI_FLAGS * dv.num_envs + env] |= SHIPENV_FLAG_TRACKER;
     }
-    ship_step<MODEL>(P, rt, 0, s, false, 0.0);
+    ship_step<MODEL>(P, rt, 0, s, false, 0.0, -0.0, 1.0);
   }
   store_ship(dv, n_ships, sidx, s);
 }
@@ -576,7 +722,7 @@ __global__ void k_init_prev_states(DevView dv) {
 // ------------------------------------------------------------------------------------------------
 enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 
-template <int MODEL, int ENVKIND, int MODE>
+template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
 __global__ void __launch_bounds__(128, SENV_MIN_BLOCKS)
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
   __shared__ SharedBlock sb;
@@ -606,6 +752,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp};
   double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0, n_base = 0.0, e_base = 0.0;
   double log_n = 0.0, log_e = 0.0;
+  double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)
   int sampling_count = 0, snapshot_info = 0, flags = 0, n_iw = 0;
   float ps_tn = 0.f, ps_te = 0.f, ps_on = 0.f, ps_oe = 0.f;
   double u_pre = 0.0;         // surge speed before the last integration (obs[6])
@@ -656,6 +803,10 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       e_base = ef[SHIPENV_EF_E_BASE * B + env];
       log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
       log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+      if (SBMPC) {
+        sb_p_last = ef[SHIPENV_EF_SB_P_LAST * B + env];
+        sb_chi_last = ef[SHIPENV_EF_SB_CHI_LAST * B + env];
+      }
       const int* ei = dv.buf.env_i32;
       sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
       snapshot_info = ei[SHIPENV_EI_SNAPSHOT_INFO * B + env];
@@ -722,9 +873,62 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     do {
     const bool running = (lstate == LS_RUN) && !finalize;
     bool st_done = false, st_terminal = false, st_roa = false;
-    if (running) {
+    // The assets step in list order (test_step, then obs_step).  The lanes of a pair run them side by
+    // side, except under SBMPC in the NonIW env, where obs_step's SBMPC call reads the state the ship under
+    // test has just integrated to (run_colav env.py:502-527): two phases there.
+    constexpr int N_PHASE = (SBMPC && !IS_IW) ? 2 : 1;
+#pragma unroll 1
+    for (int phase = 0; phase < N_PHASE; ++phase) {
+    const bool stepping = running && (N_PHASE == 1 || role == phase);
+    const bool stop_branch = stepping && has_stop_branch && s.stop;
+    double heading_offset = -0.0, speed_factor = 1.0;
+    if (SBMPC) {
+      // rl_env env.py:360-385, run_colav env.py:1145-1170 (and :371-396, :502-527 in the NonIW env)
+      const int caller_role = (N_PHASE == 1) ? 0 : phase;
+      const bool caller = stepping && !stop_branch && role == caller_role;
+      SbmpcIn in;
+      in.chi_d = 0.0;
+      // next_wpt()'s result is discarded and los_guidance runs on the autopilot's current waypoint index:
+      // the LOS integrator advances a first time here (quirk 2 of SURVEY.md section 8)
+      if (caller) in.chi_d = -los_guidance(P, s);
+      const double q_east = shfl_xor_f64(s.east, 1), q_north = shfl_xor_f64(s.north, 1);
+      const double q_yaw = shfl_xor_f64(s.yaw, 1), q_u = shfl_xor_f64(s.u, 1), q_v = shfl_xor_f64(s.v, 1);
+      // own ship = assets[0] (ship under test), obstacle = assets[1], whichever asset calls
+      in.os_x = role == 0 ? s.east : q_east; in.os_y = role == 0 ? s.north : q_north; in.os_v = role == 0 ? s.v : q_v;
+      in.ob_x = role == 1 ? s.east : q_east; in.ob_y = role == 1 ? s.north : q_north;
+      in.ob_psi = -(role == 1 ? s.yaw : q_yaw);
+      in.ob_u = role == 1 ? s.u : q_u; in.ob_v = role == 1 ? s.v : q_v;
+      in.u_d = P.desired_speed;
+      in.chi_last = sb_chi_last; in.p_last = sb_p_last;
+      bool active = false;
+      if (caller) {
+        const double d0 = in.ob_x - in.os_x, d1 = in.ob_y - in.os_y;
+        active = sqrt(d0 * d0 + d1 * d1) < 2000.0;            // D_INIT_, sbmpc.py:154-166
+        if (!active) { sb_p_last = 1.0; sb_chi_last = 0.0; }
+      }
+      unsigned todo = __ballot_sync(FULL_MASK, caller && active);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int best = sbmpc_warp_argmin(in, src, lane, G.ship[1].l_ship, G.ship[1].w_ship);
+        if (lane == src) {
+          double u_best = 1.0, chi_best = 0.0;
+          if (best >= 0) {
+            const int ic = best >> 2, jp = best & 3;
+            chi_best = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);
+            u_best = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
+          }
+          sb_p_last = u_best; sb_chi_last = chi_best;
+          speed_factor = u_best; heading_offset = -chi_best;
+        }
+      }
+      // the pair shares one SBMPC object: the other lane takes over the caller's copy of its memory
+      sb_p_last = __shfl_sync(FULL_MASK, sb_p_last, (lane & ~1) | caller_role);
+      sb_chi_last = __shfl_sync(FULL_MASK, sb_chi_last, (lane & ~1) | caller_role);
+    }
+    if (stepping) {
       const double dt = P.dt;
-      if (has_stop_branch && s.stop) {
+      if (stop_branch) {
         // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
         s.time = s.time + dt;
         s.time = s.time + dt;
@@ -739,7 +943,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           hit = (dn * dn + de * de) < 9000000.0f;
         }
         const double pre_n = s.north, pre_e = s.east;
-        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias);
+        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor);
         if (role == 1 && IS_IW) {
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
@@ -750,6 +954,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         }
         log_n = pre_n; log_e = pre_e;
       }
+    }
     }
     // ---- exchange with the other ship of the pair (all lanes participate)
     const double p_north = shfl_xor_f64(s.north, 1);
@@ -937,6 +1142,10 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           ef[SHIPENV_EF_E_BASE * B + env] = e_base;
           ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
           ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
+          if (SBMPC) {
+            ef[SHIPENV_EF_SB_P_LAST * B + env] = sb_p_last;
+            ef[SHIPENV_EF_SB_CHI_LAST * B + env] = sb_chi_last;
+          }
           int* ei = dv.buf.env_i32;
           ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
           ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot_info;
@@ -990,7 +1199,7 @@ k_ship_rollout(DevView dv, int k_steps) {
   load_ship(dv, n_ships, sidx, s);
   s.n_wp = P.n_wp;
   refresh_segment(rt, 0, s);
-  for (int i = 0; i < k_steps; ++i) ship_step<MODEL>(P, rt, 0, s, false, 0.0);
+  for (int i = 0; i < k_steps; ++i) ship_step<MODEL>(P, rt, 0, s, false, 0.0, -0.0, 1.0);
   store_ship(dv, n_ships, sidx, s);
   if (dv.buf.counters) atomicAdd(&dv.buf.counters[2], (unsigned long long)k_steps);
 }
@@ -1019,13 +1228,13 @@ cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st) {
 
 // persistent grid: as many CTAs as are resident at once (queried per instantiation), never more than
 // the environments need
-template <int MODEL, int ENVKIND, int MODE>
-static void launch_env_inst(const SenvView& v, const double* actions, int k, unsigned long long* queue,
-                            int sm_count, int persistent, cudaStream_t st) {
+template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
+static void launch_env_inst2(const SenvView& v, const double* actions, int k, unsigned long long* queue,
+                             int sm_count, int persistent, cudaStream_t st) {
   static int per_sm = 0;
   if (per_sm == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE>, kBlock, 0) != cudaSuccess || n < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE, SBMPC>, kBlock, 0) != cudaSuccess || n < 1)
       n = SENV_MIN_BLOCKS;
     per_sm = n;
   }
@@ -1033,7 +1242,14 @@ static void launch_env_inst(const SenvView& v, const double* actions, int k, uns
   const long long resident = (long long)per_sm * (sm_count > 0 ? sm_count : 148);
   // persistent: resident CTAs only, lane pairs refill from the queue; otherwise one slot per environment
   const int grid = (int)((persistent && resident < need) ? resident : need);
-  k_env<MODEL, ENVKIND, MODE><<<grid, kBlock, 0, st>>>(v, actions, k, queue);
+  k_env<MODEL, ENVKIND, MODE, SBMPC><<<grid, kBlock, 0, st>>>(v, actions, k, queue);
+}
+
+template <int MODEL, int ENVKIND, int MODE>
+static void launch_env_inst(const SenvView& v, const double* actions, int k, unsigned long long* queue,
+                            int sm_count, int persistent, cudaStream_t st) {
+  if (v.sbmpc) launch_env_inst2<MODEL, ENVKIND, MODE, true>(v, actions, k, queue, sm_count, persistent, st);
+  else launch_env_inst2<MODEL, ENVKIND, MODE, false>(v, actions, k, queue, sm_count, persistent, st);
 }
 
 template <int MODEL, int MODE>
@@ -1075,6 +1291,6 @@ cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st)
 }
 
 #else
-template __global__ void k_env<0, 1, 0>(DevView, const double*, int, unsigned long long*);
+template __global__ void k_env<0, 1, 0, false>(DevView, const double*, int, unsigned long long*);
 #endif
 }  // namespace SENV_NS

@@ -27,6 +27,7 @@ struct SenvView {
   ShipEnvBuffers buf;
   long long num_envs;
   SenvGrid grid;
+  int sbmpc;   // params->collav == SHIPENV_COLLAV_SBMPC (selects the kernel instantiation)
 };
 
 #define SENV_DECLARE(ns)                                                                                       \

@@ -92,6 +92,7 @@ def pack_ship_params(asset: ShipAssets, nav_fail_tol: float, dt_shaft: Optional[
     p.wind_speed, p.wind_dir = sm.wind_speed, sm.wind_dir
     p.cos_wind_dir, p.sin_wind_dir = float(np.cos(sm.wind_dir)), float(np.sin(sm.wind_dir))
     p.proj_area_f, p.proj_area_l, p.l_ship = sm.proj_area_f, sm.proj_area_l, sm.l_ship
+    p.w_ship = sm.w_ship
     sc = sm.simulation_config
     p.init_north, p.init_east, p.init_yaw = sc.initial_north_position_m, sc.initial_east_position_m, sc.initial_yaw_angle_rad
     p.init_u, p.init_v, p.init_r = (sc.initial_forward_speed_m_per_s, sc.initial_sideways_speed_m_per_s,
@@ -198,7 +199,7 @@ def pack_params(assets, map_obj: PolygonObstacle, args, env_kind: int, post_rese
     elif collav == 'simple':
         P.collav = L.COLLAV_SIMPLE
     elif collav == 'sbmpc':
-        raise NotImplementedError("collav_mode='sbmpc' is not built yet (SURVEY.md section 8f #1); use 'none' or 'simple'")
+        P.collav = L.COLLAV_SBMPC
     else:
         raise ValueError(f"unknown collav_mode {collav!r}")
     P.max_sampling_frequency = msf

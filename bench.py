@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=100_000, help="environments per GPU")
     ap.add_argument("--workload", default="colav_iw", choices=["colav_iw", "rl"])
+    ap.add_argument("--collav", default="none", choices=["none", "simple", "sbmpc"],
+                    help="collision avoidance of the ship under test (the headline workload uses 'none')")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "strict"], help="device code build (see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -60,11 +62,11 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_inputs(workload, envs, rank):
+def make_inputs(workload, envs, rank, collav="none"):
     """Synthetic inputs of the workload: actions [B, 9] float64 and jittered initial states."""
     import torch
     from ast_sac_b200 import scenarios as S
-    args = S.get_env_args(time_step=4, collav_mode="none")
+    args = S.get_env_args(time_step=4, collav_mode=collav)
     if workload == "rl":
         assets, m = S.build_rl_assets(args)
     else:
@@ -75,12 +77,13 @@ def make_inputs(workload, envs, rank):
     return args, assets, m, actions, init
 
 
-def workload_name(workload, envs):
+def workload_name(workload, envs, collav="none"):
+    suffix = "" if collav == "none" else f", collav_mode={collav}"
     if workload == "rl":
         return (f"rl_env MultiShipRLEnv: ShipModelAST (PTI) test+obs pair, full AST reward + map, {envs} envs/GPU, "
-                "dt=4, 9 step() per episode")
+                f"dt=4, 9 step() per episode{suffix}")
     return (f"run_colav MultiShipEnv (run_simplified_IW_model.py): SimpleShipModel test+obs pair + "
-            f"HeadingBySampledRouteController, {envs} envs/GPU, dt=4, 9 step() per episode")
+            f"HeadingBySampledRouteController, {envs} envs/GPU, dt=4, 9 step() per episode{suffix}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -137,10 +140,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_episode_rate(workload, n_episodes, threads=0, seed_rank=0):
+def cpu_episode_rate(workload, n_episodes, threads=0, seed_rank=0, collav="none"):
     """Time the CPU oracle on a bounded sample of the same workload; returns (env-steps/s, steps, secs)."""
     from oracle import oracle as O
-    args, assets, m, actions, init = make_inputs(workload, n_episodes, seed_rank)
+    args, assets, m, actions, init = make_inputs(workload, n_episodes, seed_rank, collav)
     kind = O.ENV_RL if workload == "rl" else O.ENV_COLAV_IW
     cfg = O.env_config_from_assets(assets, m, args, kind)
     init_np = init.numpy().reshape(7, n_episodes, 2)
@@ -153,9 +156,9 @@ def cpu_episode_rate(workload, n_episodes, threads=0, seed_rank=0):
     return total / dt, total, dt
 
 
-def calibrated_cpu_sample(workload, target_s=12.0):
+def calibrated_cpu_sample(workload, target_s=12.0, collav="none"):
     cores = os.cpu_count() or 1
-    rate, steps, secs = cpu_episode_rate(workload, 64 * cores)
+    rate, steps, secs = cpu_episode_rate(workload, 64 * cores, collav=collav)
     per_episode = secs / (64 * cores)
     n = int(max(64 * cores, min(400_000, target_s / max(per_episode, 1e-9))))
     return n, cores
@@ -164,12 +167,12 @@ def calibrated_cpu_sample(workload, target_s=12.0):
 def run_reference(a, rank, world):
     if rank != 0:
         return
-    n, cores = calibrated_cpu_sample(a.workload, target_s=10.0)
+    n, cores = calibrated_cpu_sample(a.workload, target_s=10.0, collav=a.collav)
     for _ in range(a.warmup):
-        cpu_episode_rate(a.workload, max(64, n // 8))
+        cpu_episode_rate(a.workload, max(64, n // 8), collav=a.collav)
     tot_steps, tot_s = 0, 0.0
     for _ in range(a.steps):
-        _, steps, secs = cpu_episode_rate(a.workload, n)
+        _, steps, secs = cpu_episode_rate(a.workload, n, collav=a.collav)
         tot_steps += steps
         tot_s += secs
     value = tot_steps / tot_s
@@ -178,7 +181,7 @@ def run_reference(a, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot_s / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a.workload, a.envs), "sample": sample},
+        "config": {"workload": workload_name(a.workload, a.envs, a.collav), "sample": sample},
         "cpu_baseline": {"value": value, "unit": METRIC, "cores": cores, "kind": "port", "sample": sample,
                          "note": "C restatement of the reference simulator (oracle/), pthreads over episodes; the "
                                  "reference itself is single-process Python (~1.4e3 env-steps/s on one core, "
@@ -209,7 +212,7 @@ def run_b200(a, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     B = a.envs
-    args, assets, m, actions_cpu, init_cpu = make_inputs(a.workload, B, rank)
+    args, assets, m, actions_cpu, init_cpu = make_inputs(a.workload, B, rank, a.collav)
     init_dev = init_cpu.to(dev)
     actions_dev = actions_cpu.to(dev)
     actions_host = np.ascontiguousarray(actions_cpu.numpy().T)          # [9, B] rows for the host API
@@ -363,7 +366,7 @@ def run_b200(a, rank, local_rank, world):
             "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * max_time / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a.workload, B), "envs_per_gpu": B, "envs_total": B * world,
+            "config": {"workload": workload_name(a.workload, B, a.collav), "envs_per_gpu": B, "envs_total": B * world,
                        "math_mode": a.math,
                        "sharding": "contiguous env blocks per rank, no per-step collective",
                        "l2": "256 MB buffer written between timed iterations (state < 126 MB L2)",
@@ -384,8 +387,8 @@ def run_b200(a, rank, local_rank, world):
                            "api": "reset_host() + 9 x step_host(): numpy actions in, numpy obs/reward/info out "
                                   "through shipenv_reset_host / shipenv_step_host (pinned staging inside the C ABI)"}
         if world == 1 and not a.no_cpu_baseline:
-            n, cores = calibrated_cpu_sample(a.workload, target_s=12.0)
-            rate, steps, secs = cpu_episode_rate(a.workload, n)
+            n, cores = calibrated_cpu_sample(a.workload, target_s=12.0, collav=a.collav)
+            rate, steps, secs = cpu_episode_rate(a.workload, n, collav=a.collav)
             line["cpu_baseline"] = {"value": rate, "unit": METRIC, "cores": cores, "kind": "port",
                                     "sample": f"{n} episodes of the same workload ({steps} env-steps, {secs:.1f} s), "
                                               f"oracle/shipsim_oracle.c on {cores} host threads"}

@@ -21,7 +21,7 @@ from oracle import oracle as O
 
 from helpers import (CTRL_SCALE, CTRL_TOL_DETAILED, REL_TOL, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
                      rel_err, struct_from_bytes)
-from product_helpers import env_from_meta, product_ctrl_vec, product_ship_vec, product_states_all
+from product_helpers import assets_from_meta, env_from_meta, product_ctrl_vec, product_ship_vec, product_states_all
 
 pytestmark = pytest.mark.gpu
 
@@ -30,6 +30,40 @@ MATH_MODES = ["strict", "fast"]     # both builds of the device code are held to
 
 def _sync():
     torch.cuda.synchronize()
+
+
+def _golden_conditioning(meta, actions):
+    """Per step() call, the largest relative state change of the ORACLE's own trajectory of this golden
+    episode when one initial state moves by one ulp (surge speed up/down, heading, shaft speed): how far
+    two IEEE-correct evaluations of the reference's formulas can legitimately drift apart (DESIGN.md
+    section 2; the detailed model's throttle cascade has gain ~1e4)."""
+    assets, m, args = assets_from_meta(meta)
+    base = O.env_config_from_assets(assets, m, args, O.ENV_RL if meta["kind"] == "rl" else O.ENV_COLAV_IW)
+    runs = []
+    for variant in range(5):
+        cfg = O.EnvConfig()
+        C.memmove(C.byref(cfg), C.byref(base), C.sizeof(O.EnvConfig))
+        for role in range(2):
+            c = cfg.ship[role]
+            if variant == 1:
+                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 10.0)
+            elif variant == 2:
+                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 0.0)
+            elif variant == 3:
+                c.initial_yaw_angle_rad = np.nextafter(c.initial_yaw_angle_rad, 10.0)
+            elif variant == 4:
+                c.initial_propeller_shaft_speed_rad_per_s = np.nextafter(c.initial_propeller_shaft_speed_rad_per_s, 0.0)
+        oe = O.OracleEnv(cfg)
+        oe.reset()
+        out = []
+        for a in actions:
+            r = oe.step(float(a))
+            out.append(np.stack([oracle_ship_vec(oe.st.ship[0]), oracle_ship_vec(oe.st.ship[1])]))
+            if r.done:
+                break
+        runs.append(out)
+    n = min(len(r) for r in runs)
+    return [max(float(rel_err(runs[0][j], runs[v][j], STATE_SCALE).max()) for v in range(1, 5)) for j in range(n)]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -46,6 +80,7 @@ def test_iw_episode_matches_reference_golden(name, math_mode):
     obs0 = env.reset()
     assert np.array_equal(np.asarray(obs0), g["obs0"])
     n = int(g["n_valid"])
+    cond = None      # oracle 1-ulp conditioning of this episode, computed only if a detailed-model state exceeds REL_TOL
     for j in range(n):
         res = env.step(np.array([g["actions"][j]]))
         if is_rl:
@@ -61,16 +96,26 @@ def test_iw_episode_matches_reference_golden(name, math_mode):
         assert info["obs_ship_stop"] == bool(g["obs_stop"][j])
         k = env.next_wpt[0].cpu().numpy()
         assert k[0] == g["k_test"][j] and k[1] == g["k_obs"][j], (name, j, k)
+        loose = 1.0      # widening of the scalar checks of this step when the conditioning allowance applies
         for role, key in ((0, "test"), (1, "obs")):
             e = rel_err(product_ship_vec(env, role), g[key + "_state"][j], STATE_SCALE)
-            assert e.max() < REL_TOL, (name, j, key, e)
+            tol, ctrl_tol = REL_TOL, (CTRL_TOL_DETAILED if detailed else REL_TOL)
+            if detailed and e.max() >= REL_TOL:
+                # the detailed model's conditioning: accept what one ulp of an initial state does to the
+                # oracle's own trajectory at this step (x10), never more than 1e-6; flags stay bit-exact
+                cond = cond or _golden_conditioning(meta, g["actions"][:n])
+                tol = min(1e-6, 10 * cond[j])
+                ctrl_tol = max(ctrl_tol, 10 * tol)
+                loose = max(loose, tol / REL_TOL)
+                print(f"[{name}/{math_mode}] step {j} {key}: err {e.max():.2e}, oracle 1-ulp conditioning {cond[j]:.2e}")
+            assert e.max() < tol, (name, j, key, e, cond)
             e = rel_err(product_ctrl_vec(env, role), g[key + "_ctrl"][j], CTRL_SCALE)
             # controller integrators of the ill-conditioned detailed model: 1e-8
-            assert e.max() < (CTRL_TOL_DETAILED if detailed else REL_TOL), (name, j, key, "ctrl", e)
-        assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < REL_TOL
-        np.testing.assert_allclose(o, g["obs"][j], rtol=2e-7, atol=1e-6)
+            assert e.max() < ctrl_tol, (name, j, key, "ctrl", e)
+        assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < REL_TOL * loose
+        np.testing.assert_allclose(o, g["obs"][j], rtol=2e-7 * loose, atol=1e-6 * loose)
         if is_rl:
-            assert rel_err(r, g["reward"][j], 1e-3) < 1e-8, (name, j, r, g["reward"][j])
+            assert rel_err(r, g["reward"][j], 1e-3) < 1e-8 * loose, (name, j, r, g["reward"][j])
     # number of simulator steps: the reference log has one row per _step() plus the init_step row
     # (a sampling failure adds none)
     assert env.total_substeps() == int(g["n_log"][n - 1]) - 1
@@ -184,7 +229,8 @@ def _oracle_sensitivity(base_cfg, init_np, b, actions_row, upto_step):
 
 
 @pytest.mark.parametrize("math_mode", MATH_MODES)
-@pytest.mark.parametrize("kind,collav", [("rl", "none"), ("colav", "none"), ("rl", "simple"), ("colav", "simple")])
+@pytest.mark.parametrize("kind,collav", [("rl", "none"), ("colav", "none"), ("rl", "simple"), ("colav", "simple"),
+                                         ("rl", "sbmpc"), ("colav", "sbmpc")])
 def test_batched_episodes_match_oracle(kind, collav, math_mode):
     """256 environments, per-env random scoping angles and jittered start positions, full episodes
     (9 step() calls); every environment is compared with its own scalar oracle run.
@@ -270,6 +316,68 @@ def test_batched_episodes_match_oracle(kind, collav, math_mode):
     print(f"[{kind}/{collav}/{math_mode}] worst rel err of well-conditioned envs {worst:.2e}; ill-conditioned envs: {ill}")
     # the batch must have exercised several different endings
     assert bin(seen_events).count("1") >= 5, bin(seen_events)
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["rl", "colav"])
+def test_sbmpc_memory_survives_reset(kind):
+    """SBMPCParams.P_ca_last_ / Chi_ca_last_ belong to the env's single SBMPC object: reset() does not
+    clear them (sbmpc.py:30-31, env.py:123, 238-295), so the first SBMPC call of a second episode is
+    penalised against the last manoeuvre of the first.  64 environments on a collision course, two
+    episodes back to back, each compared with its own oracle."""
+    B = 64
+    args = S.get_env_args(time_step=4, collav_mode="sbmpc")
+    if kind == "rl":
+        assets, m = S.build_rl_assets(args)
+        init = S.jittered_init_states(assets, B, pos_jitter_m=50.0, seed=11)
+        env, assets = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+        okind = O.ENV_RL
+    else:
+        assets, m = S.build_colav_assets(args, iw=True)
+        init = S.jittered_init_states(assets, B, pos_jitter_m=50.0, seed=11)
+        env, assets = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init)
+        okind = O.ENV_COLAV_IW
+    gen = torch.Generator().manual_seed(4)
+    actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6) * 0.08
+    init_np = init.cpu().numpy().reshape(7, B, 2)
+    base_cfg = _oracle_cfg(assets, env, okind)
+    oracles = []
+    for b in range(B):
+        cfg = O.EnvConfig()
+        C.memmove(C.byref(cfg), C.byref(base_cfg), C.sizeof(O.EnvConfig))
+        for role in range(2):
+            cfg.ship[role].initial_north_position_m = init_np[0, b, role]
+            cfg.ship[role].initial_east_position_m = init_np[1, b, role]
+        oracles.append(O.OracleEnv(cfg))
+    carried = 0
+    for episode in range(2):
+        env.reset()
+        for oe in oracles:
+            oe.reset()
+        if episode == 1:
+            sb = env.env_f64[[L.EF["sb_p_last"], L.EF["sb_chi_last"]]].cpu().numpy()
+            for b, oe in enumerate(oracles):
+                assert sb[0, b] == oe.st.sb_p_last and sb[1, b] == oe.st.sb_chi_last
+            carried = int(((sb[0] != 1.0) | (sb[1] != 0.0)).sum())
+        alive = np.ones(B, dtype=bool)
+        for j in range(9):
+            env.step(actions[:, j].cuda())
+            _sync()
+            info = env.info_buf.cpu().numpy()
+            nsub = env.nsub_buf.cpu().numpy()
+            states = product_states_all(env)
+            for b in range(B):
+                if not alive[b]:
+                    continue
+                r = oracles[b].step(float(actions[b, j]))
+                assert nsub[b] == r.n_substeps and (info[b] & L.INFO_EVENT_MASK) == r.events, (episode, b, j)
+                if kind == "colav":     # the detailed model's conditioning is covered by the test above
+                    for role in range(2):
+                        e = rel_err(states[b, role], oracle_ship_vec(oracles[b].st.ship[role]), STATE_SCALE)
+                        assert e.max() < REL_TOL, (episode, b, j, role, e)
+                if r.done:
+                    alive[b] = False
+    assert carried > 0, "no environment ended its first episode in the middle of an SBMPC manoeuvre"
     env.close()
 
 

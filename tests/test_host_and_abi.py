@@ -106,10 +106,15 @@ def test_pack_params_derived_constants():
     assert P2.ship[0].dt_shaft == 0.01 and P2.ship[1].dt_shaft == 0.01
 
 
-def test_pack_params_rejects_sbmpc_and_bad_routes():
-    args = S.get_env_args(collav_mode='sbmpc')
-    assets, m = S.build_rl_assets(args)
-    with pytest.raises(NotImplementedError):
+def test_pack_params_collav_modes_and_bad_routes():
+    for mode, code in (('none', L.COLLAV_NONE), ('simple', L.COLLAV_SIMPLE), ('sbmpc', L.COLLAV_SBMPC)):
+        args = S.get_env_args(collav_mode=mode)
+        assets, m = S.build_rl_assets(args)
+        P = E.pack_params(assets, m, args, L.ENV_RL, post_reset=True)
+        assert P.collav == code
+        assert P.ship[1].w_ship == assets[1].ship_model.w_ship and P.ship[1].l_ship == assets[1].ship_model.l_ship
+    args = S.get_env_args(collav_mode='mpc')
+    with pytest.raises(ValueError):
         E.pack_params(assets, m, args, L.ENV_RL, post_reset=True)
     with pytest.raises((OSError, FileNotFoundError)):      # same exception type as the reference's np.loadtxt
         from ast_sac_b200.sim.LOS_guidance import NavigationSystem
