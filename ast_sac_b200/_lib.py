@@ -76,7 +76,7 @@ EXPORTS = [
     "shipenv_layout", "shipenv_bind", "shipenv_alloc", "shipenv_buffers", "shipenv_set_params",
     "shipenv_construct", "shipenv_reset", "shipenv_init_step", "shipenv_step", "shipenv_substeps",
     "shipenv_ship_rollout", "shipenv_reset_host", "shipenv_step_host", "shipenv_substeps_host",
-    "shipenv_read_counters", "shipenv_measure_fp64_peak",
+    "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math",
 ]
 
 _lib = None
@@ -112,6 +112,7 @@ def load():
     L.shipenv_substeps_host.argtypes = [vp, i32, vp, vp, vp, vp]
     L.shipenv_read_counters.argtypes = [vp, vp]
     L.shipenv_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
+    L.shipenv_selftest_math.argtypes = [i32, i64, C.c_uint64, vp]
     if L.shipenv_abi_version() != ABI_VERSION:
         raise ImportError("libshipenv.so ABI version mismatch; rebuild the extension")
     if L.shipenv_sizeof_params() != C.sizeof(Params):
@@ -125,6 +126,13 @@ def measure_fp64_peak(device: int = 0, repeats: int = 5) -> float:
     out = C.c_double()
     check(load().shipenv_measure_fp64_peak(device, repeats, C.byref(out)))
     return out.value
+
+
+def selftest_math(device: int = 0, n: int = 1 << 24, seed: int = 1):
+    """(sincos, atan) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA math library: fast build, strict build."""
+    out = (C.c_ulonglong * 4)()
+    check(load().shipenv_selftest_math(device, n, seed, out))
+    return list(out)
 
 
 def check(rc: int):

@@ -57,6 +57,10 @@ struct shipenv {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
+  // caller buffers of the *_host entry points that were page-locked with cudaHostRegister: the copies then
+  // go straight between the caller's memory and the device (no staging memcpy)
+  struct HostReg { const void* ptr; size_t bytes; bool ok; };
+  std::vector<HostReg> host_regs;
 };
 
 namespace {
@@ -273,18 +277,42 @@ Pinned pinned_view(shipenv* h) {
   return v;
 }
 
+// Is [ptr, ptr + bytes) page-locked?  Buffers of at least 256 KiB are registered on first use (callers such as
+// a rollout loop pass the same arrays every step, so the registration is paid once); small or unregistrable
+// buffers go through the pinned staging area instead.
+bool host_locked(shipenv* h, const void* ptr, size_t bytes) {
+  for (const auto& r : h->host_regs)
+    if (r.ptr == ptr && r.bytes >= bytes) return r.ok;
+  bool ok = false;
+  if (bytes >= (256u << 10) && h->host_regs.size() < 64) {
+    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
+    if (e == cudaSuccess) ok = true;
+    else if (e == cudaErrorHostMemoryAlreadyRegistered) { ok = true; cudaGetLastError(); }
+    else cudaGetLastError();   // not registrable (e.g. read-only mapping): use the staging path
+  }
+  if (h->host_regs.size() < 64) h->host_regs.push_back({ptr, bytes, ok});
+  return ok;
+}
+
 int fetch_outputs(shipenv* h, float* obs_host, double* reward_host, int32_t* info_host, int32_t* nsub_host) {
   const size_t B = (size_t)h->num_envs;
   Pinned pv = pinned_view(h);
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(pv.obs, h->buf.obs_f32, B * 32, cudaMemcpyDeviceToHost, h->stream));
-  if (reward_host) CUDA_TRY(cudaMemcpyAsync(pv.reward, h->buf.reward, B * 8, cudaMemcpyDeviceToHost, h->stream));
-  if (info_host) CUDA_TRY(cudaMemcpyAsync(pv.info, h->buf.info_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
-  if (nsub_host) CUDA_TRY(cudaMemcpyAsync(pv.nsub, h->buf.nsub_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
+  const bool d_obs = obs_host && host_locked(h, obs_host, B * 32);
+  const bool d_rew = reward_host && host_locked(h, reward_host, B * 8);
+  const bool d_info = info_host && host_locked(h, info_host, B * 4);
+  const bool d_nsub = nsub_host && host_locked(h, nsub_host, B * 4);
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(d_obs ? obs_host : pv.obs, h->buf.obs_f32, B * 32, cudaMemcpyDeviceToHost, h->stream));
+  if (reward_host)
+    CUDA_TRY(cudaMemcpyAsync(d_rew ? reward_host : pv.reward, h->buf.reward, B * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (info_host)
+    CUDA_TRY(cudaMemcpyAsync(d_info ? info_host : pv.info, h->buf.info_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (nsub_host)
+    CUDA_TRY(cudaMemcpyAsync(d_nsub ? nsub_host : pv.nsub, h->buf.nsub_i32, B * 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
-  if (obs_host) memcpy(obs_host, pv.obs, B * 32);
-  if (reward_host) memcpy(reward_host, pv.reward, B * 8);
-  if (info_host) memcpy(info_host, pv.info, B * 4);
-  if (nsub_host) memcpy(nsub_host, pv.nsub, B * 4);
+  if (obs_host && !d_obs) memcpy(obs_host, pv.obs, B * 32);
+  if (reward_host && !d_rew) memcpy(reward_host, pv.reward, B * 8);
+  if (info_host && !d_info) memcpy(info_host, pv.info, B * 4);
+  if (nsub_host && !d_nsub) memcpy(nsub_host, pv.nsub, B * 4);
   return SHIPENV_OK;
 }
 
@@ -353,6 +381,9 @@ int shipenv_destroy(shipenv_t* h) {
   cudaFree(h->mask_dev);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
+  for (const auto& r : h->host_regs)
+    if (r.ok) cudaHostUnregister(const_cast<void*>(r.ptr));
+  cudaGetLastError();   // a buffer the caller already freed / unregistered is not an error of destroy
   delete h;
   return SHIPENV_OK;
 }
@@ -523,8 +554,12 @@ int shipenv_step_host(shipenv_t* h, const double* actions_host, float* obs_host,
   rc = ensure_staging(h);
   if (rc) return rc;
   Pinned pv = pinned_view(h);
-  memcpy(pv.actions, actions_host, (size_t)h->num_envs * 8);
-  CUDA_TRY(cudaMemcpyAsync(h->act_dev, pv.actions, (size_t)h->num_envs * 8, cudaMemcpyHostToDevice, h->stream));
+  const void* src = actions_host;
+  if (!host_locked(h, actions_host, (size_t)h->num_envs * 8)) {
+    memcpy(pv.actions, actions_host, (size_t)h->num_envs * 8);
+    src = pv.actions;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->act_dev, src, (size_t)h->num_envs * 8, cudaMemcpyHostToDevice, h->stream));
   rc = shipenv_step(h, h->act_dev, h->stream);
   if (rc) return rc;
   return fetch_outputs(h, obs_host, reward_host, info_host, nsub_host);
@@ -549,6 +584,22 @@ int shipenv_read_counters(shipenv_t* h, unsigned long long* out_host) {
   if (!h->buf.counters) return fail(SHIPENV_E_STATE, "no counters buffer bound");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpy(out_host, h->buf.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SHIPENV_OK;
+}
+
+int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long long* mismatches_host) {
+  if (!mismatches_host || n <= 0) return fail(SHIPENV_E_ARG, "bad arguments");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
+  CUDA_TRY(cudaSetDevice(device));
+  unsigned long long* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(dev, 0, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(senv_fast::launch_math_selftest(n, seed, dev, nullptr));
+  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 2, nullptr));
+  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(dev);
   return SHIPENV_OK;
 }
 

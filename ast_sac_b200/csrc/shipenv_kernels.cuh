@@ -44,6 +44,8 @@ namespace SENV_NS {
 constexpr unsigned FULL_MASK = 0xffffffffu;
 constexpr double kPi = 3.141592653589793;
 
+#include "shipenv_math.cuh"
+
 using MapGrid = SenvGrid;
 using DevView = SenvView;
 
@@ -85,7 +87,7 @@ __device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship&
   route_wp(rt, n_iw, s.k, s.wn, s.we);
   const double dx = s.wn - s.pn, dy = s.we - s.pe;
   s.alpha = atan2(dy, dx);                                   // LOS_guidance.py:105-107
-  sincos(s.alpha, &s.sin_a, &s.cos_a);
+  senv_sincos(s.alpha, &s.sin_a, &s.cos_a);
 }
 
 __device__ __forceinline__ double sat(double val, double low, double hi) {   // controllers.py:67-72
@@ -106,11 +108,11 @@ __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship&
   const double R = P.los_r;
   if (e_ct * e_ct >= R * R) e_ct = 0.99 * R;
   s.e_ct = e_ct;
-  double delta = sqrt(R * R - e_ct * e_ct);
+  double delta = SENV_SQRT(R * R - e_ct * e_ct);
   if (!(delta > 1e-6)) delta = 1e-6;
-  const double q = e_ct / delta;
+  const double q = SENV_DIV(e_ct, delta);
   if (fabs(s.e_ct_int + q) <= P.los_limit) s.e_ct_int += q;
-  const double chi_r = atan(-q - s.e_ct_int * P.los_ki);
+  const double chi_r = senv_atan(-q - s.e_ct_int * P.los_ki);
   return s.alpha + chi_r;
 }
 
@@ -179,7 +181,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   }
   // --- kinematics
   double spsi, cpsi;
-  sincos(s.yaw, &spsi, &cpsi);
+  senv_sincos(s.yaw, &spsi, &cpsi);
   const double u = s.u, v = s.v, r = s.r;
   const double d_north = cpsi * u + (-spsi) * v;
   const double d_east = spsi * u + cpsi * v;
@@ -217,7 +219,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double sw = P.sin_wind_dir * cpsi - P.cos_wind_dir * spsi;
   const double u_rw = P.wind_speed * cw - u;
   const double v_rw = P.wind_speed * sw - v;
-  const double vmag = sqrt(u_rw * u_rw + v_rw * v_rw);
+  const double vmag = SENV_SQRT(u_rw * u_rw + v_rw * v_rw);
   const double tau_u = (-0.3 * P.proj_area_f) * vmag * u_rw;
   const double tau_v = (-0.42 * P.proj_area_l) * vmag * v_rw;
   const double tau_n = (-0.096 * P.proj_area_l * P.l_ship) * u_rw * v_rw;
@@ -872,7 +874,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     // ---------------- (3) simulator steps of the running lanes, until some pair has finished its call
     do {
     const bool running = (lstate == LS_RUN) && !finalize;
-    bool st_done = false, st_terminal = false, st_roa = false;
     // The assets step in list order (test_step, then obs_step).  The lanes of a pair run them side by
     // side, except under SBMPC in the NonIW env, where obs_step's SBMPC call reads the state the ship under
     // test has just integrated to (run_colav env.py:502-527): two phases there.
@@ -948,7 +949,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
             const double tn = pre_n - log_n, te = pre_e - log_e;
-            travel_dist += sqrt(tn * tn + te * te);
+            travel_dist += SENV_SQRT(tn * tn + te * te);
             travel_time += dt;
           }
         }
@@ -956,12 +957,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
     }
     }
-    // ---- exchange with the other ship of the pair (all lanes participate)
+    // ---- the ships meet: positions both ways, then one word of partial flags per ship.  Almost every
+    // simulator step is "quiet" (no termination / stop condition holds for either ship, no collision, no
+    // radius of acceptance reached): those steps skip the event bookkeeping below altogether.
     const double p_north = shfl_xor_f64(s.north, 1);
     const double p_east = shfl_xor_f64(s.east, 1);
-    const double p_yaw = shfl_xor_f64(s.yaw, 1);
-    const double p_time = shfl_xor_f64(s.time, 1);
-    // own partial flags / rewards
+    // bits of my_flags: 1 grounding, 2 navigation failure, 4 reached the route end, 8 outside the map horizon,
+    // 16 simulation time limit (set by the test lane), 32 radius of acceptance reached (set by the obstacle lane)
     int my_flags = 0;
     double ra = 0.0, rb = 0.0;
     if (running) {
@@ -978,6 +980,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       bool nav_fail = fabs(s.e_ct) > P.nav_fail_tol;
       if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
+      // is_within_simu_time_limit on the test ship's clock (check_condition.py:206-213)
+      if (role == 0 && s.time > P.sim_time) my_flags |= 16;
+      if (MODE == MODE_STEP && role == 1 && stage == 0) {
+        // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
+        const double rn = s.north - s.wn, re = s.east - s.we;
+        if ((rn * rn + re * re) < G.roa * G.roa) my_flags |= 32;
+      }
       if (IS_RL) {
         const double gd = map_distance(mp, s.north, s.east);
         const double aect = fabs(s.e_ct);
@@ -993,89 +1002,96 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
     }
     const int p_flags = __shfl_xor_sync(FULL_MASK, my_flags, 1);
+    const int p_stop = __shfl_xor_sync(FULL_MASK, s.stop, 1);
     double p_ra = 0.0, p_rb = 0.0;
     if (IS_RL) { p_ra = shfl_xor_f64(ra, 1); p_rb = shfl_xor_f64(rb, 1); }
 
     if (running) {
       nsub += 1;
-      const double t_n = role == 0 ? s.north : p_north, t_e = role == 0 ? s.east : p_east;
-      const double t_yaw = role == 0 ? s.yaw : p_yaw, t_time = role == 0 ? s.time : p_time;
-      const double o_n = role == 1 ? s.north : p_north, o_e = role == 1 ? s.east : p_east;
       const int t_flags = role == 0 ? my_flags : p_flags, o_flags = role == 1 ? my_flags : p_flags;
       if (G.collav == SHIPENV_COLLAV_SIMPLE) {   // self.states = next_states (float32)
+        const double t_n = role == 0 ? s.north : p_north, t_e = role == 0 ? s.east : p_east;
+        const double o_n = role == 1 ? s.north : p_north, o_e = role == 1 ? s.east : p_east;
         ps_tn = (float)t_n; ps_te = (float)t_e; ps_on = (float)o_n; ps_oe = (float)o_e;
       }
-      // ship-ship terms (compute_distance.py:16-40, check_condition.py:142-158)
-      const double dx = o_n - t_n, dy = o_e - t_e;
+      // ship-ship terms (compute_distance.py:16-40, check_condition.py:142-158); (a - b)^2 == (b - a)^2
+      // exactly, so both lanes get the same d2
+      const double dx = p_north - s.north, dy = p_east - s.east;       // obs - test on the test lane
       const double d2 = dx * dx + dy * dy;
       const bool is_collision = d2 < 2500.0;
-      const bool t_ground = t_flags & 1, t_nav = t_flags & 2, o_ground = o_flags & 1, o_nav = o_flags & 2;
+      // The AST reward is accumulated on the TEST lane only (role 0: it has the test ship's heading for the
+      // encounter type); the obstacle lane's r_total / acc_reward are never read (it fetches them from its
+      // partner when the environment is stored).
       double r_total = 0.0;
       if (IS_RL) {
         const double distance = sqrt(d2);
         double r1 = 0.0;
         if (distance < 10000.0) {
           const double phi = atan2(dy, dx);
-          double beta = phi - t_yaw;
+          double beta = phi - s.yaw;
           beta = py_mod(beta + kPi, 2 * kPi) - kPi;
           const bool overtaking = !(fabs(beta) < 15.0 * (kPi / 180.0)) && (fabs(beta) > 165.0 * (kPi / 180.0));
           // head-on or crossing -> RewardDesign4(target 0, 2e8); the "overtake" branch is dead code
           if (!overtaking) r1 = (distance < 0.0) ? 1.0 : exp(-(distance * distance) / 200000000.0);
         }
-        const double t_ra = role == 0 ? ra : p_ra, t_rb = role == 0 ? rb : p_rb;
-        const double o_ra = role == 1 ? ra : p_ra, o_rb = role == 1 ? rb : p_rb;
-        r_total = ((((r1 + t_ra) + t_rb) + o_ra) + o_rb) / 5;
-        // get_reward_due_to_ships_termination (reward_function.py:272-314)
-        if (is_collision || t_ground || t_nav || o_ground || o_nav) {
-          const double reward = r_total + acc_reward;
-          r_total = 0;
-          if (acc_reward > 0) {
-            if (is_collision) r_total += reward * 10.0;
-            if (t_ground) r_total += reward * 5.0;
-            if (t_nav) r_total += reward * 5.0;
-            if (o_ground) r_total += reward * -2.5;
-            if (o_nav) r_total += reward * -2.5;
-          } else if (acc_reward < 0) {
-            if (is_collision) r_total += reward * -10.0;
-            if (t_ground) r_total += reward * -5.0;
-            if (t_nav) r_total += reward * -5.0;
-            if (o_ground) r_total += reward * 2.5;
-            if (o_nav) r_total += reward * 2.5;
+        r_total = ((((r1 + ra) + rb) + p_ra) + p_rb) / 5;               // test terms, then obstacle terms
+      }
+      bool st_done = false, st_terminal = false;
+      out_info = 0;
+      if (((t_flags | o_flags) & 31) != 0 || is_collision) {
+        // ---- something holds: termination reward, events and env_info (reward_function.py:204-314)
+        const bool t_ground = t_flags & 1, t_nav = t_flags & 2, o_ground = o_flags & 1, o_nav = o_flags & 2;
+        if (IS_RL) {
+          // get_reward_due_to_ships_termination (reward_function.py:272-314)
+          if (is_collision || t_ground || t_nav || o_ground || o_nav) {
+            const double reward = r_total + acc_reward;
+            r_total = 0;
+            if (acc_reward > 0) {
+              if (is_collision) r_total += reward * 10.0;
+              if (t_ground) r_total += reward * 5.0;
+              if (t_nav) r_total += reward * 5.0;
+              if (o_ground) r_total += reward * -2.5;
+              if (o_nav) r_total += reward * -2.5;
+            } else if (acc_reward < 0) {
+              if (is_collision) r_total += reward * -10.0;
+              if (t_ground) r_total += reward * -5.0;
+              if (t_nav) r_total += reward * -5.0;
+              if (o_ground) r_total += reward * 2.5;
+              if (o_nav) r_total += reward * 2.5;
+            }
           }
         }
+        int ev = 0;
+        bool terminal = false, ts = false, os = false;
+        if (is_collision) { ev |= SHIPENV_EV_COLLISION; terminal = ts = os = true; }
+        if (t_ground) { ev |= SHIPENV_EV_TEST_GROUNDING; terminal = ts = true; }
+        if (t_nav) { ev |= SHIPENV_EV_TEST_NAV_FAILURE; terminal = ts = true; }
+        if (o_ground) { ev |= SHIPENV_EV_OBS_GROUNDING; terminal = os = true; }
+        if (o_nav) { ev |= SHIPENV_EV_OBS_NAV_FAILURE; terminal = os = true; }
+        if (t_flags & 4) { ev |= SHIPENV_EV_TEST_REACHED; ts = true; }
+        if (t_flags & 8) { ev |= SHIPENV_EV_TEST_OUTSIDE; ts = true; }
+        if (o_flags & 4) { ev |= SHIPENV_EV_OBS_REACHED; os = true; }
+        if (o_flags & 8) { ev |= SHIPENV_EV_OBS_OUTSIDE; os = true; }
+        if (t_flags & 16) { ev |= SHIPENV_EV_TIME_LIMIT; ts = os = true; }
+        st_terminal = terminal;
+        int partner_stop = p_stop;
+        if (IS_RL) {                                              // rl_env env.py:603-610
+          st_done = ts && !terminal;
+          if (role == 1 && os && !terminal) s.stop = 1;
+        } else {                                                  // run_colav env.py:1385-1399
+          if (ts && !terminal) { if (role == 0) s.stop = 1; else partner_stop = 1; }
+          if (os && !terminal) { if (role == 1) s.stop = 1; else partner_stop = 1; }
+          st_done = s.stop && partner_stop;                       // done needs both stop flags
+        }
+        out_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
+                   (os ? SHIPENV_INFO_OBS_STOP : 0);
+      } else if (!IS_RL) {
+        st_done = s.stop && p_stop;
       }
-      // events and env_info (reward_function.py:204-268)
-      int ev = 0;
-      bool terminal = false, ts = false, os = false;
-      if (is_collision) { ev |= SHIPENV_EV_COLLISION; terminal = ts = os = true; }
-      if (t_ground) { ev |= SHIPENV_EV_TEST_GROUNDING; terminal = ts = true; }
-      if (t_nav) { ev |= SHIPENV_EV_TEST_NAV_FAILURE; terminal = ts = true; }
-      if (o_ground) { ev |= SHIPENV_EV_OBS_GROUNDING; terminal = os = true; }
-      if (o_nav) { ev |= SHIPENV_EV_OBS_NAV_FAILURE; terminal = os = true; }
-      if (t_flags & 4) { ev |= SHIPENV_EV_TEST_REACHED; ts = true; }
-      if (t_flags & 8) { ev |= SHIPENV_EV_TEST_OUTSIDE; ts = true; }
-      if (o_flags & 4) { ev |= SHIPENV_EV_OBS_REACHED; os = true; }
-      if (o_flags & 8) { ev |= SHIPENV_EV_OBS_OUTSIDE; os = true; }
-      if (t_time > G.ship[0].sim_time) { ev |= SHIPENV_EV_TIME_LIMIT; ts = os = true; }
-      st_terminal = terminal;
-      if (IS_RL) {                                              // rl_env env.py:603-610
-        st_done = ts && !terminal;
-        if (role == 1 && os && !terminal) s.stop = 1;
-      } else {                                                  // run_colav env.py:1385-1399
-        if (role == 0 && ts && !terminal) s.stop = 1;
-        if (role == 1 && os && !terminal) s.stop = 1;
-        // done needs both stop flags: resolved after the shuffle below
-      }
-      out_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
-                 (os ? SHIPENV_INFO_OBS_STOP : 0);
       if (IS_RL) {
         if (MODE == MODE_STEP) acc_reward += r_total;
         out_reward = r_total;
       }
-    }
-    const int p_stop = __shfl_xor_sync(FULL_MASK, s.stop, 1);
-    if (running) {
-      if (!IS_RL) st_done = s.stop && p_stop;
       const bool combined_done = st_terminal || st_done;
       if (combined_done) out_info |= SHIPENV_INFO_DONE;
       if (MODE == MODE_SUBSTEPS) {
@@ -1086,11 +1102,12 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       } else {
         // step() control flow: rl_env env.py:700-771, run_colav env.py:1478-1533
         if (stage == 0) {
-          // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
-          // (meaningful on the obstacle lane; the test lane receives it below)
-          const double dn = s.north - s.wn, de = s.east - s.we;
-          st_roa = (dn * dn + de * de) < G.roa * G.roa;
           if (combined_done) { have_obs = true; flags |= SHIPENV_FLAG_DONE; finalize = true; }
+          else if (o_flags & 32) {
+            // the obstacle ship is inside the radius of acceptance of its next waypoint
+            if (have_iw) stage = 1;
+            else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finalize = true; }
+          }
         } else if (stage == 1) {
           have_obs = true;
           if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
@@ -1100,14 +1117,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           have_obs = true;
           if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
         }
-      }
-    }
-    if (MODE == MODE_STEP) {
-      // RoA flag lives on the obstacle lane (role 1): broadcast it to the pair
-      const int is_roa = __shfl_sync(FULL_MASK, (int)st_roa, lane | 1);
-      if (running && !finalize && stage == 0 && is_roa) {
-        if (have_iw) stage = 1;
-        else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finalize = true; }
       }
     }
     } while (!__any_sync(FULL_MASK, finalize || lstate == LS_FETCH));
@@ -1125,6 +1134,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
       const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
       const float t2 = __shfl_xor_sync(FULL_MASK, o2, 1);
+      if (IS_RL) {
+        // the reward accumulators live on the test lane; the obstacle lane writes the environment
+        const double acc_t = shfl_xor_f64(acc_reward, 1), out_t = shfl_xor_f64(out_reward, 1);
+        if (role == 1) { acc_reward = acc_t; out_reward = out_t; }
+      }
       if (finalize) {
         store_ship(dv, n_ships, 2 * env + role, s);
         if (role == 1) {
@@ -1281,6 +1295,12 @@ cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, con
     if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
     else launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned long long* mismatches_dev,
+                                 cudaStream_t st) {
+  k_math_selftest<<<(int)((n + 255) / 256), 256, 0, st>>>(n, seed, mismatches_dev);
   return cudaGetLastError();
 }
 

@@ -510,7 +510,10 @@ class BatchedShipEnv:
         if not self._post_reset:
             self.reset()
             torch.cuda.current_stream(self._device).synchronize()
-        obs = np.empty((B, 8), np.float32)
+        if not hasattr(self, "_host_reset_obs"):
+            # one persistent array: the C ABI page-locks caller buffers it sees repeatedly
+            self._host_reset_obs = np.empty((B, 8), np.float32)
+        obs = self._host_reset_obs
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)

@@ -323,9 +323,10 @@ def test_batched_episodes_match_oracle(kind, collav, math_mode):
 def test_sbmpc_memory_survives_reset(kind):
     """SBMPCParams.P_ca_last_ / Chi_ca_last_ belong to the env's single SBMPC object: reset() does not
     clear them (sbmpc.py:30-31, env.py:123, 238-295), so the first SBMPC call of a second episode is
-    penalised against the last manoeuvre of the first.  64 environments on a collision course, two
-    episodes back to back, each compared with its own oracle."""
+    penalised against the last manoeuvre of the first.  64 environments on a collision course, an
+    abandoned episode followed by a full one, each environment compared with its own oracle."""
     B = 64
+    n_first = 6 if kind == "rl" else 9      # step() calls of the first episode
     args = S.get_env_args(time_step=4, collav_mode="sbmpc")
     if kind == "rl":
         assets, m = S.build_rl_assets(args)
@@ -360,7 +361,8 @@ def test_sbmpc_memory_survives_reset(kind):
                 assert sb[0, b] == oe.st.sb_p_last and sb[1, b] == oe.st.sb_chi_last
             carried = int(((sb[0] != 1.0) | (sb[1] != 0.0)).sum())
         alive = np.ones(B, dtype=bool)
-        for j in range(9):
+        # (rl) the first episode is abandoned after 6 step() calls, while the ships are passing each other
+        for j in range(n_first if episode == 0 else 9):
             env.step(actions[:, j].cuda())
             _sync()
             info = env.info_buf.cpu().numpy()
