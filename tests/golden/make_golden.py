@@ -263,5 +263,72 @@ def main():
     save("colav_noniw_dt4_reset", noniw_run(4, use_reset=True))
 
 
+# ------------------------------------------------------------------------------------------------
+# sampler goldens: the reference's own ast_sac_rollout through its NormalizedBoxEnv
+# ------------------------------------------------------------------------------------------------
+SAMPLER_POLICIES = {   # a = tanh(w3 * obs[3] + w4 * obs[4] + w5 * obs[5] + b), evaluated in float32
+    "sampler_rl_dt4_pol0": (0.00012, -0.00009, 0.3, 0.35),
+    "sampler_rl_dt4_pol1": (0.00002, -0.00003, 0.05, 0.25),
+    "sampler_rl_dt4_pol2": (-0.00001, 0.00002, -0.02, -0.1),
+    "sampler_rl_dt4_sbmpc_pol1": (0.00002, -0.00003, 0.05, 0.25),
+}
+
+
+class LinearTanhPolicy:
+    """Deterministic stand-in for the TanhGaussian policy: float32 arithmetic, action in [-1, 1]."""
+
+    def __init__(self, w):
+        self.w = [np.float32(x) for x in w]
+
+    def reset(self):
+        pass
+
+    def get_action(self, o):
+        o = np.asarray(o, dtype=np.float32)
+        z = self.w[0] * o[3] + self.w[1] * o[4] + self.w[2] * o[5] + self.w[3]
+        return np.array([np.tanh(z)], dtype=np.float32), {}
+
+
+def sampler_golden(w, collav="none", reward_scale=0.75, max_path_length=9):
+    from ast_sac.samplers.data_collector.rollout_functions import ast_sac_rollout
+    from ast_sac.env_wrapper.normalized_box_env import NormalizedBoxEnv
+    import copy
+    env, _ = H.make_rl_env(H.Args(time_step=4, collav_mode=collav))
+
+    class Recording(NormalizedBoxEnv):
+        """Keeps a copy of every env_info at the time step() returned it: the reference appends the env's own
+        snapshot dict to the path, and the sampling-failure branch (rl_env env.py:673-693) later mutates that
+        same object, so path['env_infos'][-2] is retroactively overwritten."""
+        infos = []
+
+        def step(self, action):
+            out = super().step(action)
+            self.infos.append(copy.deepcopy(out[3]))
+            return out
+
+    wrapped = Recording(env, reward_scale=reward_scale)
+    wrapped.infos = []
+    path = ast_sac_rollout(wrapped, LinearTanhPolicy(w), max_path_length=max_path_length)
+    path["env_infos"] = wrapped.infos
+    meta = dict(kind="rl", dt=4, collav=collav, reward_scale=reward_scale, max_path_length=max_path_length, w=list(w))
+    return dict(meta=json.dumps(meta), observations=np.asarray(path["observations"], dtype=np.float32),
+                actions=np.asarray(path["actions"], dtype=np.float32), rewards=np.asarray(path["rewards"], dtype=np.float64),
+                next_observations=np.asarray(path["next_observations"], dtype=np.float32),
+                terminals=np.asarray(path["terminals"]).astype(np.uint8), dones=np.asarray(path["dones"]).astype(np.uint8),
+                events=np.array([events_bits(i["events"]) for i in path["env_infos"]], dtype=np.int32))
+
+
+def main_sampler():
+    H.install_stubs()
+    for name, w in SAMPLER_POLICIES.items():
+        out = sampler_golden(w, collav="sbmpc" if "sbmpc" in name else "none")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, len(out["actions"]), out["actions"].ravel(), out["events"][-1])
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sampler":
+        main_sampler()      # only the sampler fixtures (the others are unchanged)
+    else:
+        main()
+        main_sampler()

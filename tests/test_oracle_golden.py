@@ -124,3 +124,36 @@ def test_struct_sizes_and_kat_numbers():
                                               4.362949147831841, 0.7831900869036864, -0.0015340263572957782],
                                rtol=1e-10)
     assert wpt[0] == 1 and wpt[99] == 1 and wpt[999] == 4
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler goldens: the reference's ast_sac_rollout through its NormalizedBoxEnv
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("sampler_"))
+def test_oracle_follows_reference_sampler_episode(name):
+    """The rollout loop of rollout_functions.py:109-150 restated on the oracle env: float32 policy action ->
+    NormalizedBoxEnv scaling in float32 (normalized_box_env.py:46-57) -> step().  The reference evaluates
+    tan() of the float32 scoping angle in float32, the oracle in float64 (quirk 12 of SURVEY.md section 8):
+    the sampled waypoints differ by <= 1e-7 relative, hence the looser tolerances here."""
+    import json
+    from product_helpers import assets_from_meta
+    g = golden(name)
+    meta = json.loads(str(g["meta"]))
+    assets, m, args = assets_from_meta(meta)
+    env = O.OracleEnv(O.env_config_from_assets(assets, m, args, O.ENV_RL))
+    env.reset()
+    w = [np.float32(x) for x in meta["w"]]
+    lb, ub = np.float32(-np.deg2rad(30)), np.float32(np.deg2rad(30))
+    o = np.array(env.st.initial_states[:], dtype=np.float32)
+    n = len(g["actions"])
+    for j in range(n):
+        a = np.tanh(w[0] * o[3] + w[1] * o[4] + w[2] * o[5] + w[3]).astype(np.float32)
+        assert abs(float(a) - float(g["actions"][j, 0])) < 1e-5, (name, j)
+        scaled = np.clip(lb + (a + np.float32(1.0)) * np.float32(0.5) * (ub - lb), lb, ub)
+        r = env.step(float(scaled))
+        np.testing.assert_allclose(np.array(r.obs[:]), g["next_observations"][j], rtol=1e-5, atol=0.05)
+        assert abs(r.reward * meta["reward_scale"] - g["rewards"][j, 0]) < 1e-4 * max(1.0, abs(g["rewards"][j, 0]))
+        assert bool(r.terminal) == bool(g["terminals"][j, 0]) and bool(r.done) == bool(g["dones"][j, 0])
+        assert r.events == g["events"][j]
+        o = np.array(r.obs[:], dtype=np.float32)
+    assert bool(g["dones"][n - 1, 0]) or n == meta["max_path_length"]
