@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 4
+ABI_VERSION = 5
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED = 0, 1
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
@@ -23,8 +23,9 @@ INFO_EVENT_MASK = 0x7ff
 INFO_TERMINAL, INFO_TEST_STOP, INFO_OBS_STOP, INFO_DONE, INFO_UNBOUND = 1 << 16, 1 << 17, 1 << 18, 1 << 19, 1 << 20
 
 SF = dict(north=0, east=1, yaw=2, u=3, v=4, r=5, omega=6, time=7, e_ct=8, e_ct_int=9, hdg_err_i=10,
-          hdg_prev_err=11, spd_err_i=12, spd_aux=13)
-SF_COUNT = 14
+          hdg_prev_err=11, spd_err_i=12, spd_aux=13, seg_alpha=14, seg_sin=15, seg_cos=16)
+SF_COUNT = 17
+LOG_COLS = ("time", "north", "east", "yaw", "rudder", "u", "v", "r", "omega", "cmd", "e_ct", "e_psi")
 EF = dict(travel_dist=0, travel_time=1, acc_reward=2, n_base=3, e_base=4, log_north=5, log_east=6, sb_p_last=7,
           sb_chi_last=8)
 EF_COUNT = 9
@@ -76,7 +77,7 @@ EXPORTS = [
     "shipenv_layout", "shipenv_bind", "shipenv_alloc", "shipenv_buffers", "shipenv_set_params",
     "shipenv_construct", "shipenv_reset", "shipenv_init_step", "shipenv_step", "shipenv_substeps",
     "shipenv_ship_rollout", "shipenv_reset_host", "shipenv_step_host", "shipenv_substeps_host",
-    "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math",
+    "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math", "shipenv_set_trajectory_log",
 ]
 
 _lib = None
@@ -111,6 +112,7 @@ def load():
     L.shipenv_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.shipenv_substeps_host.argtypes = [vp, i32, vp, vp, vp, vp]
     L.shipenv_read_counters.argtypes = [vp, vp]
+    L.shipenv_set_trajectory_log.argtypes = [vp, vp, vp, i64, i64]
     L.shipenv_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.shipenv_selftest_math.argtypes = [i32, i64, C.c_uint64, vp]
     if L.shipenv_abi_version() != ABI_VERSION:

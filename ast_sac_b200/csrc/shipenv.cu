@@ -48,6 +48,9 @@ struct shipenv {
   unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
   int sm_count = 0;
+  double* log_dev = nullptr;          // optional trajectory log (caller-owned), see shipenv_set_trajectory_log
+  int32_t* log_count_dev = nullptr;
+  long long log_envs = 0, log_capacity = 0;
   unsigned* grid_dev = nullptr;       // culling grid cells
   unsigned long long* edges_dev = nullptr;   // per-cell ring-segment masks
   SenvGrid grid{};
@@ -99,7 +102,8 @@ int validate(const ShipEnvParams* p, long long num_envs) {
 }
 
 SenvView view(const shipenv* h) {
-  return SenvView{h->params_dev, h->buf, h->num_envs, h->grid, h->params.collav == SHIPENV_COLLAV_SBMPC ? 1 : 0};
+  return SenvView{h->params_dev, h->buf, h->num_envs, h->grid, h->params.collav == SHIPENV_COLLAV_SBMPC ? 1 : 0,
+                  h->log_dev, h->log_count_dev, h->log_envs, h->log_capacity};
 }
 
 int check_ready(const shipenv* h, bool need_constructed) {
@@ -125,6 +129,13 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   // once a noticeable share is done, a persistent grid whose lane pairs refill from the work queue
   // wins (finished environments cost one fetch instead of an idle lane pair).  The share comes from the
   // previous launch's count (copied to pinned memory without a sync, so it may lag by a launch).
+  if (mode == 0) {
+    // step(action): the per-environment prologue first, at full width (csrc/shipenv_kernels.cuh k_prologue)
+    cudaError_t pe = (h->params.math_mode == SHIPENV_MATH_FAST)
+                         ? senv_fast::launch_prologue(view(h), h->params.env_kind, actions, st)
+                         : senv_strict::launch_prologue(view(h), h->params.env_kind, actions, st);
+    if (pe != cudaSuccess) return fail(SHIPENV_E_CUDA, "prologue kernel launch: %s", cudaGetErrorString(pe));
+  }
   int persistent = h->persist_mode;
   if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
@@ -575,6 +586,17 @@ int shipenv_substeps_host(shipenv_t* h, int k, float* obs_host, double* reward_h
   rc = shipenv_substeps(h, k, h->stream);
   if (rc) return rc;
   return fetch_outputs(h, obs_host, reward_host, info_host, nsub_host);
+}
+
+int shipenv_set_trajectory_log(shipenv_t* h, double* log_dev, int32_t* count_dev, int64_t log_envs, int64_t capacity) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  if (!log_dev || !count_dev || log_envs <= 0 || capacity <= 0) {
+    h->log_dev = nullptr; h->log_count_dev = nullptr; h->log_envs = 0; h->log_capacity = 0;
+    return SHIPENV_OK;
+  }
+  if (log_envs > h->num_envs) return fail(SHIPENV_E_ARG, "log_envs %lld > num_envs %lld", (long long)log_envs, h->num_envs);
+  h->log_dev = log_dev; h->log_count_dev = count_dev; h->log_envs = log_envs; h->log_capacity = capacity;
+  return SHIPENV_OK;
 }
 
 int shipenv_read_counters(shipenv_t* h, unsigned long long* out_host) {

@@ -82,9 +82,14 @@ __device__ __forceinline__ void route_wp(const Route& rt, int n_iw, int idx, dou
   else { n = rt.file_n[head]; e = rt.file_e[head]; }
 }
 
-__device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship& s) {
+// end points of the current segment (the bearing and its sin / cos come from the cache rows of ship_f64)
+__device__ __forceinline__ void load_segment_points(const Route& rt, int n_iw, Ship& s) {
   route_wp(rt, n_iw, s.k - 1, s.pn, s.pe);
   route_wp(rt, n_iw, s.k, s.wn, s.we);
+}
+
+__device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship& s) {
+  load_segment_points(rt, n_iw, s);
   const double dx = s.wn - s.pn, dy = s.we - s.pe;
   s.alpha = atan2(dy, dx);                                   // LOS_guidance.py:105-107
   senv_sincos(s.alpha, &s.sin_a, &s.cos_a);
@@ -121,7 +126,7 @@ __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship&
 template <int MODEL>
 __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
                                           bool collav_hit, double collav_bias, double heading_offset,
-                                          double speed_factor) {
+                                          double speed_factor, double* log_row = nullptr) {
   // --- NavigationSystem.next_wpt
   {
     const double dn = s.wn - s.north, de = s.we - s.east;
@@ -178,6 +183,14 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     cmd = (cmd < 0.0) ? 0.0 : ((cmd > 1.1) ? 1.1 : cmd);
     rudder += collav_bias;
     rudder = (rudder < -P.max_rudder) ? -P.max_rudder : ((rudder > P.max_rudder) ? P.max_rudder : rudder);
+  }
+  // --- store_simulation_data (ship_model.py:418-429): the row is logged before the integration
+  if (log_row) {
+    log_row[SHIPENV_LOG_TIME] = s.time; log_row[SHIPENV_LOG_NORTH] = s.north; log_row[SHIPENV_LOG_EAST] = s.east;
+    log_row[SHIPENV_LOG_YAW] = s.yaw; log_row[SHIPENV_LOG_RUDDER] = rudder; log_row[SHIPENV_LOG_U] = s.u;
+    log_row[SHIPENV_LOG_V] = s.v; log_row[SHIPENV_LOG_R] = s.r; log_row[SHIPENV_LOG_OMEGA] = s.omega;
+    log_row[SHIPENV_LOG_CMD] = cmd; log_row[SHIPENV_LOG_E_CT] = s.e_ct;
+    log_row[SHIPENV_LOG_E_PSI] = fabs(s.yaw - heading_ref);            // get_heading_error, controllers.py:396-397
   }
   // --- kinematics
   double spsi, cpsi;
@@ -571,8 +584,37 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
   __syncthreads();
 }
 
+// trajectory log (shipenv_set_trajectory_log): next row of ship `sidx`, or nullptr when the ship is not logged
+// or its log is full; log_n < 0 means "not logged"
+__device__ __forceinline__ double* log_next_row(const DevView& dv, long long sidx, int& log_n) {
+  if (log_n < 0) return nullptr;
+  double* row = (log_n < dv.log_capacity)
+                    ? dv.log_f64 + ((long long)sidx * dv.log_capacity + log_n) * SHIPENV_LOG_COLS : nullptr;
+  log_n += 1;
+  return row;
+}
+
+// store_last_simulation_data (ship_model.py:433-445): the previous row again, with the current time
+__device__ __forceinline__ void log_repeat_row(const DevView& dv, long long sidx, int& log_n, double time) {
+  if (log_n < 0) return;
+  if (log_n > 0 && log_n < dv.log_capacity) {
+    double* row = dv.log_f64 + ((long long)sidx * dv.log_capacity + log_n) * SHIPENV_LOG_COLS;
+    const double* prev = row - SHIPENV_LOG_COLS;
+    for (int c = 0; c < SHIPENV_LOG_COLS; ++c) row[c] = prev[c];
+    row[SHIPENV_LOG_TIME] = time;
+  }
+  log_n += 1;
+}
+
+__device__ __forceinline__ int log_begin(const DevView& dv, long long env, long long sidx) {
+  return (dv.log_f64 && env < dv.log_envs) ? dv.log_count[sidx] : -1;
+}
+
 __device__ __forceinline__ void load_ship(const DevView& dv, long long n_ships, long long sidx, Ship& s) {
   const double* f = dv.buf.ship_f64;
+  s.alpha = f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx];
+  s.sin_a = f[SHIPENV_SF_SEG_SIN * n_ships + sidx];
+  s.cos_a = f[SHIPENV_SF_SEG_COS * n_ships + sidx];
   s.north = f[SHIPENV_SF_NORTH * n_ships + sidx];
   s.east = f[SHIPENV_SF_EAST * n_ships + sidx];
   s.yaw = f[SHIPENV_SF_YAW * n_ships + sidx];
@@ -608,6 +650,9 @@ __device__ __forceinline__ void store_ship(const DevView& dv, long long n_ships,
   f[SHIPENV_SF_HDG_PREV_ERR * n_ships + sidx] = s.hdg_prev_err;
   f[SHIPENV_SF_SPD_ERR_I * n_ships + sidx] = s.spd_err_i;
   f[SHIPENV_SF_SPD_AUX * n_ships + sidx] = s.spd_aux;
+  f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx] = s.alpha;
+  f[SHIPENV_SF_SEG_SIN * n_ships + sidx] = s.sin_a;
+  f[SHIPENV_SF_SEG_COS * n_ships + sidx] = s.cos_a;
   dv.buf.ship_i32[sidx] = (s.k & 0xff) | (s.stop << 8);
 }
 
@@ -654,8 +699,11 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
   Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
            dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * dv.num_envs + env : nullptr, dv.num_envs, P.n_wp};
   Ship s;
+  int log_n = -1;
   if (reinit) {
     init_ship_regs(P, init_dev, n_ships, sidx, s);
+    refresh_segment(rt, 0, s);
+    if (dv.log_f64 && env < dv.log_envs) { dv.log_count[sidx] = 0; log_n = 0; }   // simulation_results = defaultdict(list)
     // obs rows <- initial_states (env.py:107-110); built from both ships of the pair
     float* orow = dv.buf.obs_f32 + env * 8;
     if (role == 0) { orow[0] = (float)s.north; orow[1] = (float)s.east; orow[2] = 0.0f; }
@@ -685,17 +733,20 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
     }
   } else {
     load_ship(dv, n_ships, sidx, s);
-    s.n_wp = P.n_wp + (dynamic_route ? dv.buf.env_i32[SHIPENV_EI_SAMPLING_COUNT * dv.num_envs + env] : 0);
+    const int n_iw = dynamic_route ? dv.buf.env_i32[SHIPENV_EI_SAMPLING_COUNT * dv.num_envs + env] : 0;
+    s.n_wp = P.n_wp + n_iw;
+    load_segment_points(rt, n_iw, s);
+    log_n = log_begin(dv, env, sidx);
   }
   if (do_init_step) {
     // init_step (env.py:297-342): controllers, log row, one integration step, tracker on
-    refresh_segment(rt, 0, s);
     if (role == 1) {
       dv.buf.env_f64[SHIPENV_EF_LOG_NORTH * dv.num_envs + env] = s.north;
       dv.buf.env_f64[SHIPENV_EF_LOG_EAST * dv.num_envs + env] = s.east;
       dv.buf.env_i32[SHIPENV_EI_FLAGS * dv.num_envs + env] |= SHIPENV_FLAG_TRACKER;
     }
-    ship_step<MODEL>(P, rt, 0, s, false, 0.0, -0.0, 1.0);
+    ship_step<MODEL>(P, rt, s.n_wp - P.n_wp, s, false, 0.0, -0.0, 1.0, log_next_row(dv, sidx, log_n));
+    if (log_n >= 0) dv.log_count[sidx] = log_n;
   }
   store_ship(dv, n_ships, sidx, s);
 }
@@ -710,6 +761,95 @@ __global__ void k_init_prev_states(DevView dv) {
   dv.buf.prev_f32[1 * dv.num_envs + env] = orow[1];
   dv.buf.prev_f32[2 * dv.num_envs + env] = orow[3];
   dv.buf.prev_f32[3 * dv.num_envs + env] = orow[4];
+}
+
+// ------------------------------------------------------------------------------------------------
+// step(action) prologue, one thread per environment (rl_env env.py:641-696, run_colav env.py:1430-1474):
+// obs_ship_uses_scoping_angle -> get_intermediate_waypoints -> update_route -> sampling-failure test.
+// Runs before k_env<MODE_STEP> on the same stream, at full lane utilisation (inside the persistent env
+// kernel this work ran for one lane pair of a warp at a time).  An environment whose sampled waypoint fails
+// the test is finished here (it returns its results snapshot unchanged); for the others the obstacle ship's
+// segment cache is refreshed when the insertion changed the waypoint it is heading for.
+// ------------------------------------------------------------------------------------------------
+template <int ENVKIND>
+__global__ void __launch_bounds__(128)
+k_prologue(DevView dv, const double* __restrict__ actions) {
+  __shared__ SharedBlock sb;
+  stage_params(sb, dv.params);
+  const ShipEnvParams& G = sb.p;
+  const long long B = dv.num_envs;
+  const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= B) return;
+  constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
+  int* ei = dv.buf.env_i32;
+  double* ef = dv.buf.env_f64;
+  int flags = ei[SHIPENV_EI_FLAGS * B + env];
+  if (flags & SHIPENV_FLAG_DONE) return;                      // k_env reports it as already done
+  flags &= ~SHIPENV_FLAG_HAVE_IW;
+  int sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
+  if (sampling_count < G.max_sampling_frequency) {
+    const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
+    const double a = actions[env];
+    sampling_count += 1;
+    // get_intermediate_waypoints (env.py:198-236)
+    const double n_base = ef[SHIPENV_EF_N_BASE * B + env], e_base = ef[SHIPENV_EF_E_BASE * B + env];
+    const double l_s = fabs(G.ab_segment_length * tan(a));
+    double e_s = l_s * G.cos_omega;
+    double n_s = l_s * G.sin_omega;
+    if (a > 0) e_s *= -1; else n_s *= -1;
+    const double rn = n_base + n_s, re = e_base + e_s;
+    ef[SHIPENV_EF_N_BASE * B + env] = rn + G.ab_north_segment_length;
+    ef[SHIPENV_EF_E_BASE * B + env] = re + G.ab_east_segment_length;
+    // update_route: insert before the last waypoint (controllers.py:417-422)
+    dv.buf.iw_f64[(long long)(sampling_count - 1) * B + env] = rn;
+    dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + sampling_count - 1) * B + env] = re;
+    ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
+    ef[SHIPENV_EF_TRAVEL_DIST * B + env] = 0.0;
+    ef[SHIPENV_EF_TRAVEL_TIME * B + env] = 0.0;
+    flags |= SHIPENV_FLAG_HAVE_IW;
+    // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
+    const bool fail = map_contains(mp, map_cell_masks(mp, rn, re) & 0xffffu, rn, re) ||
+                      ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
+    if (fail) {
+      double out_reward = 0.0;
+      if (IS_RL) {
+        const double acc = ef[SHIPENV_EF_ACC_REWARD * B + env];    // reward_function.py:499-527, multiplier 2
+        out_reward = (acc >= 0) ? (-acc * 2.0) : (acc * 2.0);
+      }
+      const int snapshot = (ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] & 0x7ff) | SHIPENV_EV_SAMPLING_FAILURE |
+                           SHIPENV_INFO_TERMINAL;
+      ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot;
+      dv.buf.info_i32[env] = snapshot | SHIPENV_INFO_DONE;
+      dv.buf.reward[env] = out_reward;
+      dv.buf.nsub_i32[env] = 0;
+      flags |= SHIPENV_FLAG_DONE;
+      if (dv.buf.counters) atomicAdd(&dv.buf.counters[1], 1ull);
+    } else {
+      if (IS_RL) ef[SHIPENV_EF_ACC_REWARD * B + env] = 0.0;      // rl_env env.py:696
+      // The new waypoint took the route's second-to-last slot.  If the obstacle ship is already heading for
+      // the route's last waypoint (index head + n_iw_old), that index now holds the new waypoint.
+      const ShipEnvShipParams& P = G.ship[1];
+      const long long n_ships = 2 * B, sidx = 2 * env + 1;
+      const int k = dv.buf.ship_i32[sidx] & 0xff;
+      const int head = P.n_wp - 1;
+      if (k == head + sampling_count - 1) {
+        double pn, pe;
+        if (k - 1 < head) { pn = P.wp_north[k - 1]; pe = P.wp_east[k - 1]; }
+        else {
+          pn = dv.buf.iw_f64[(long long)(k - 1 - head) * B + env];
+          pe = dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + k - 1 - head) * B + env];
+        }
+        const double alpha = atan2(re - pe, rn - pn);               // LOS_guidance.py:105-107
+        double sa, ca;
+        senv_sincos(alpha, &sa, &ca);
+        double* f = dv.buf.ship_f64;
+        f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx] = alpha;
+        f[SHIPENV_SF_SEG_SIN * n_ships + sidx] = sa;
+        f[SHIPENV_SF_SEG_COS * n_ships + sidx] = ca;
+      }
+    }
+  }
+  ei[SHIPENV_EI_FLAGS * B + env] = flags;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -752,10 +892,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   Ship s = Ship{};
   s.k = 1;
   Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp};
-  double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0, n_base = 0.0, e_base = 0.0;
+  double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0;
   double log_n = 0.0, log_e = 0.0;
+  int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
   double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)
-  int sampling_count = 0, snapshot_info = 0, flags = 0, n_iw = 0;
+  int sampling_count = 0, flags = 0, n_iw = 0;
   float ps_tn = 0.f, ps_te = 0.f, ps_on = 0.f, ps_oe = 0.f;
   double u_pre = 0.0;         // surge speed before the last integration (obs[6])
   bool last_stop_branch = false;
@@ -793,7 +934,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
 
     // ---------------- (2) load the environment and run the step(action) prologue
     bool finalize = false;                // store this environment at the end of the iteration
-    bool write_snapshot_only = false;
     if (lstate == LS_LOAD) {
       const long long sidx = 2 * env + role;
       load_ship(dv, n_ships, sidx, s);
@@ -801,8 +941,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
       travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
       acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
-      n_base = ef[SHIPENV_EF_N_BASE * B + env];
-      e_base = ef[SHIPENV_EF_E_BASE * B + env];
       log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
       log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
       if (SBMPC) {
@@ -811,7 +949,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
       const int* ei = dv.buf.env_i32;
       sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
-      snapshot_info = ei[SHIPENV_EI_SNAPSHOT_INFO * B + env];
       flags = ei[SHIPENV_EI_FLAGS * B + env];
       if (G.collav == SHIPENV_COLLAV_SIMPLE) {
         ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
@@ -832,43 +969,14 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         if (role == 1) dv.buf.nsub_i32[env] = 0;
         lstate = LS_FETCH;
       } else if (MODE == MODE_STEP) {
-        // ---- step(action) prologue: rl_env env.py:641-696, run_colav env.py:1430-1474
-        if (sampling_count < G.max_sampling_frequency) {
-          const double a = actions[env];
-          sampling_count += 1;
-          // get_intermediate_waypoints (env.py:198-236)
-          const double l_s = fabs(G.ab_segment_length * tan(a));
-          double e_s = l_s * G.cos_omega;
-          double n_s = l_s * G.sin_omega;
-          if (a > 0) e_s *= -1; else n_s *= -1;
-          const double rn = n_base + n_s, re = e_base + e_s;
-          n_base = rn + G.ab_north_segment_length;
-          e_base = re + G.ab_east_segment_length;
-          if (role == 1) {
-            // update_route: insert before the last waypoint (controllers.py:417-422)
-            dv.buf.iw_f64[(long long)(sampling_count - 1) * B + env] = rn;
-            dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + sampling_count - 1) * B + env] = re;
-            n_iw = sampling_count;
-            s.n_wp = P.n_wp + n_iw;
-          }
-          travel_dist = 0.0; travel_time = 0.0;
-          have_iw = true;
-          // is_route_inside_obstacles / is_route_outside_horizon (check_condition.py:80-119)
-          const bool fail = map_contains(mp, map_cell_masks(mp, rn, re) & 0xffffu, rn, re) ||
-                            ((rn < G.map_min_n || rn > G.map_max_n) || (re < G.map_min_e || re > G.map_max_e));
-          if (fail) {
-            if (IS_RL) out_reward = (acc_reward >= 0) ? (-acc_reward * 2.0) : (acc_reward * 2.0);
-            snapshot_info = (snapshot_info & 0x7ff) | SHIPENV_EV_SAMPLING_FAILURE | SHIPENV_INFO_TERMINAL;
-            out_info = snapshot_info | SHIPENV_INFO_DONE;
-            flags |= SHIPENV_FLAG_DONE;
-            write_snapshot_only = true;      // obs row (the snapshot) is returned unchanged
-            finalize = true;
-          } else if (IS_RL) {
-            acc_reward = 0.0;
-          }
-        }
+        // the step(action) prologue (action -> intermediate waypoint, route insertion, sampling-failure test)
+        // already ran for every environment in k_prologue
+        have_iw = (flags & SHIPENV_FLAG_HAVE_IW) != 0;
       }
-      if (lstate == LS_RUN && !finalize) refresh_segment(rt, n_iw, s);
+      if (lstate == LS_RUN) {
+        load_segment_points(rt, n_iw, s);
+        tlog_n = log_begin(dv, env, sidx);
+      }
     }
 
     // ---------------- (3) simulator steps of the running lanes, until some pair has finished its call
@@ -931,6 +1039,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       const double dt = P.dt;
       if (stop_branch) {
         // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
+        log_repeat_row(dv, 2 * env + role, tlog_n, s.time);
         s.time = s.time + dt;
         s.time = s.time + dt;
         last_stop_branch = true;
@@ -944,7 +1053,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           hit = (dn * dn + de * de) < 9000000.0f;
         }
         const double pre_n = s.north, pre_e = s.east;
-        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor);
+        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
+                         log_next_row(dv, 2 * env + role, tlog_n));
         if (role == 1 && IS_IW) {
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
@@ -1141,34 +1251,31 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
       if (finalize) {
         store_ship(dv, n_ships, 2 * env + role, s);
+        if (tlog_n >= 0) dv.log_count[2 * env + role] = tlog_n;
         if (role == 1) {
+          int* ei = dv.buf.env_i32;
           if (have_obs) {
             float4* orow = reinterpret_cast<float4*>(dv.buf.obs_f32 + env * 8);
             orow[0] = make_float4(t0, t1, t2, o0);
             orow[1] = IS_IW ? make_float4(o1, o2, o3, o4) : make_float4(o1, o2, 0.f, 0.f);
-            snapshot_info = out_info & ~SHIPENV_INFO_DONE;
+            ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = out_info & ~SHIPENV_INFO_DONE;     // results snapshot
           }
           double* ef = dv.buf.env_f64;
           ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
           ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
           ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
-          ef[SHIPENV_EF_N_BASE * B + env] = n_base;
-          ef[SHIPENV_EF_E_BASE * B + env] = e_base;
           ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
           ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
           if (SBMPC) {
             ef[SHIPENV_EF_SB_P_LAST * B + env] = sb_p_last;
             ef[SHIPENV_EF_SB_CHI_LAST * B + env] = sb_chi_last;
           }
-          int* ei = dv.buf.env_i32;
-          ei[SHIPENV_EI_SAMPLING_COUNT * B + env] = sampling_count;
-          ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = snapshot_info;
           ei[SHIPENV_EI_FLAGS * B + env] = flags;
           if (G.collav == SHIPENV_COLLAV_SIMPLE) {
             dv.buf.prev_f32[0 * B + env] = ps_tn; dv.buf.prev_f32[1 * B + env] = ps_te;
             dv.buf.prev_f32[2 * B + env] = ps_on; dv.buf.prev_f32[3 * B + env] = ps_oe;
           }
-          if (IS_RL && MODE == MODE_STEP && !write_snapshot_only) out_reward = acc_reward;
+          if (IS_RL && MODE == MODE_STEP) out_reward = acc_reward;
           dv.buf.reward[env] = out_reward;
           dv.buf.info_i32[env] = out_info;
           dv.buf.nsub_i32[env] = nsub;
@@ -1212,8 +1319,10 @@ k_ship_rollout(DevView dv, int k_steps) {
   Ship s;
   load_ship(dv, n_ships, sidx, s);
   s.n_wp = P.n_wp;
-  refresh_segment(rt, 0, s);
-  for (int i = 0; i < k_steps; ++i) ship_step<MODEL>(P, rt, 0, s, false, 0.0, -0.0, 1.0);
+  load_segment_points(rt, 0, s);
+  int log_n = log_begin(dv, sidx >> 1, sidx);
+  for (int i = 0; i < k_steps; ++i) ship_step<MODEL>(P, rt, 0, s, false, 0.0, -0.0, 1.0, log_next_row(dv, sidx, log_n));
+  if (log_n >= 0) dv.log_count[sidx] = log_n;
   store_ship(dv, n_ships, sidx, s);
   if (dv.buf.counters) atomicAdd(&dv.buf.counters[2], (unsigned long long)k_steps);
 }
@@ -1280,6 +1389,13 @@ static void launch_env_kind(const SenvView& v, int env_kind, const double* actio
       launch_env_inst<MODEL, SHIPENV_ENV_RL, MODE>(v, actions, k, queue, sm_count, persistent, st);
       break;
   }
+}
+
+cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, cudaStream_t st) {
+  const int grid = (int)((v.num_envs + kBlock - 1) / kBlock);
+  if (env_kind == SHIPENV_ENV_RL) k_prologue<SHIPENV_ENV_RL><<<grid, kBlock, 0, st>>>(v, actions);
+  else k_prologue<SHIPENV_ENV_COLAV_IW><<<grid, kBlock, 0, st>>>(v, actions);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,

@@ -28,6 +28,10 @@ struct SenvView {
   long long num_envs;
   SenvGrid grid;
   int sbmpc;   // params->collav == SHIPENV_COLLAV_SBMPC (selects the kernel instantiation)
+  // optional trajectory log (shipenv_set_trajectory_log)
+  double* log_f64;
+  int32_t* log_count;
+  long long log_envs, log_capacity;
 };
 
 #define SENV_DECLARE(ns)                                                                                       \
@@ -35,6 +39,7 @@ struct SenvView {
   cudaError_t launch_reset(const SenvView& v, int model, const uint8_t* mask, const double* init, int do_init, \
                            int reinit, cudaStream_t st);                                                       \
   cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st);                                            \
+  cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, cudaStream_t st);        \
   cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,   \
                          unsigned long long* queue, int sm_count, int persistent, cudaStream_t st);            \
   cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st);                            \

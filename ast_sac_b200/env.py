@@ -329,7 +329,7 @@ class BatchedShipEnv:
     def __getstate__(self):
         d = {k: v for k, v in self.__dict__.items() if k not in (
             "_handle", "_params", "ship_f64", "ship_i32", "env_f64", "env_i32", "iw_f64", "prev_f32", "obs_buf",
-            "reward_buf", "info_buf", "nsub_buf", "counters")}
+            "reward_buf", "info_buf", "nsub_buf", "counters", "log_f64", "log_count", "_log_envs")}
         d["_device"] = str(self._device)
         return d
 
@@ -411,6 +411,65 @@ class BatchedShipEnv:
         north = [float(x) for x in nav.north[:-1]] + iw[0].tolist() + [float(nav.north[-1])]
         east = [float(x) for x in nav.east[:-1]] + iw[1].tolist() + [float(nav.east[-1])]
         return north, east
+
+    def set_done(self, mask):
+        """Mark the masked environments as finished: step() / _step() leave them untouched (and they cost the
+        kernel one queue fetch) until they are reset.  Used by the vectorised sampler to park the environments
+        it does not need for the current wave."""
+        m = torch.as_tensor(mask, device=self._device).to(torch.bool).reshape(-1)
+        if m.numel() != self.num_envs:
+            raise ValueError("mask must have num_envs entries")
+        flags = self.env_i32[L.EI["flags"]]
+        flags.copy_(torch.where(m, flags | 1, flags))
+
+    # -- trajectory log (SURVEY.md section 8f #4) ----------------------------------------------------
+    def enable_trajectory_log(self, n_envs: int = 1, capacity: int = 4096):
+        """Record the per-step rows the reference keeps in ``ship_model.simulation_results``
+        (store_simulation_data / store_last_simulation_data, ship_model.py:418-445) for the first ``n_envs``
+        environments, up to ``capacity`` rows per ship and episode (reset() restarts the log)."""
+        n_envs = int(min(n_envs, self.num_envs))
+        self.log_f64 = torch.zeros((2 * n_envs, int(capacity), len(L.LOG_COLS)), dtype=torch.float64, device=self._device)
+        self.log_count = torch.zeros((2 * n_envs,), dtype=torch.int32, device=self._device)
+        L.check(L.load().shipenv_set_trajectory_log(self._handle, self.log_f64.data_ptr(), self.log_count.data_ptr(),
+                                                     n_envs, int(capacity)))
+        self._log_envs = n_envs
+
+    def disable_trajectory_log(self):
+        torch.cuda.synchronize(self._device)
+        L.check(L.load().shipenv_set_trajectory_log(self._handle, None, None, 0, 0))
+        self._log_envs = 0
+
+    def trajectory(self, role: int, env: int = 0) -> np.ndarray:
+        """[rows, len(LOG_COLS)] raw log of one ship: columns ``_lib.LOG_COLS`` in SI units, values as logged by
+        the reference (before the integration of the step)."""
+        if not getattr(self, "_log_envs", 0) or env >= self._log_envs:
+            raise RuntimeError("trajectory logging is not enabled for this environment (enable_trajectory_log)")
+        i = 2 * env + role
+        n = min(int(self.log_count[i].item()), self.log_f64.shape[1])
+        return self.log_f64[i, :n].cpu().numpy()
+
+    def simulation_results(self, role: int, env: int = 0) -> dict:
+        """The log of one ship under the reference's ``simulation_results`` keys and units (the state and
+        controller columns; the fuel / power bookkeeping columns of ship_model.py:911-937 are derived quantities
+        off the step path and are not reproduced)."""
+        t = self.trajectory(role, env)
+        c = {n: t[:, i] for i, n in enumerate(L.LOG_COLS)}
+        deg = 180 / np.pi
+        out = {
+            'time [s]': c["time"], 'north position [m]': c["north"], 'east position [m]': c["east"],
+            'yaw angle [deg]': c["yaw"] * deg, 'rudder angle [deg]': c["rudder"] * deg,
+            'forward speed [m/s]': c["u"], 'sideways speed [m/s]': c["v"], 'yaw rate [deg/sec]': c["r"] * deg,
+        }
+        p = self._params.ship[role]
+        if p.model_kind == L.MODEL_DETAILED:
+            out['propeller shaft speed [rpm]'] = c["omega"] * 30 / np.pi
+            out['commanded load fraction [-]'] = c["cmd"]
+            out['thrust force [kN]'] = p.thrust_coeff * c["omega"] * np.abs(c["omega"]) / 1000      # ship_engine.py:411-414
+        else:
+            out['thrust force [kN]'] = c["cmd"]          # the reference logs newtons under this key (ship_model.py:427)
+        out['cross track error [m]'] = c["e_ct"]
+        out['heading error [deg]'] = c["e_psi"]          # radians in the reference too (controllers.py:396-397)
+        return {k: v.tolist() for k, v in out.items()}
 
     def do_normalize_action(self, a_real):       # env.py:186-190
         return 2.0 * (a_real - self.action_space.low) / (self.action_space.high - self.action_space.low) - 1.0

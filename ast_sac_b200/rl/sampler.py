@@ -69,6 +69,8 @@ def batched_ast_sac_rollout(env, agent, max_path_length: int, replay_buffer=None
     B = obs.shape[0]
     dev = obs.device
     alive = torch.ones(B, dtype=torch.bool, device=dev) if active is None else active.to(dev).clone()
+    if active is not None and hasattr(env, "set_done"):
+        env.set_done(~alive)                       # environments this wave does not need are parked, not simulated
     O, A, R, NO, T, D, V, E = [], [], [], [], [], [], [], []
     for _ in range(int(max_path_length)):
         a = agent.get_actions(obs, deterministic=deterministic) if deterministic else agent.get_actions(obs)

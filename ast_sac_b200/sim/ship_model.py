@@ -102,6 +102,13 @@ class BaseShipModel:
                 env, role = binding
                 return env.read_ship_state(role)[rows[name]]
             return self.__dict__["_init_state"][name]
+        if name == "simulation_results":
+            # the reference's per-step log (ship_model.py:418-429 / rl_env :903-942) of environment 0, available
+            # after env.enable_trajectory_log()
+            binding = self.__dict__.get("_binding")
+            if binding is not None:
+                env, role = binding
+                return env.simulation_results(role)
         raise AttributeError(name)
 
     def __getstate__(self):

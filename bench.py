@@ -42,7 +42,7 @@ N_RL_STEPS = 9
 FLOP_ALGO = {"colav_iw": 370.0 + 26.0, "rl": 450.0 + 31.0}
 FLOP_EXEC = {"colav_iw": 599.0, "rl": 1150.0}     # profiles/r01_ncu_summary.md section 2 (fast build)
 # HBM bytes per env-step when every simulator step is its own launch (K = 1): DESIGN.md section 4
-BYTES_K1 = 2 * (2 * (14 * 8 + 4) + 7 * 8 + 3 * 4) + 32 + 8 + 4 + 4
+BYTES_K1 = 2 * 2 * (17 * 8 + 4) + 2 * (5 * 8 + 2 * 4) + 32 + 8 + 4 + 4     # ship rows r+w, env rows r+w, outputs = 704 B (ABI v5)
 
 
 def parse_args():
@@ -310,7 +310,8 @@ def run_b200(a, rank, local_rank, world):
         l2_flush.fill_(1.0)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
-        env._step(1)
+        # the C ABI entry point itself (env._step() adds torch ops that build the info tensors)
+        L.check(L.load().shipenv_substeps(env._handle, 1, env._stream_ptr()))
         e.record(stream)
         torch.cuda.synchronize(dev)
         k1_ms.append(s.elapsed_time(e))

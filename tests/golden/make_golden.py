@@ -318,6 +318,44 @@ def sampler_golden(w, collav="none", reward_scale=0.75, max_path_length=9):
                 events=np.array([events_bits(i["events"]) for i in path["env_infos"]], dtype=np.int32))
 
 
+# ------------------------------------------------------------------------------------------------
+# trajectory-log goldens: the reference's simulation_results of one KAT episode
+# ------------------------------------------------------------------------------------------------
+LOG_KEYS = ['time [s]', 'north position [m]', 'east position [m]', 'yaw angle [deg]', 'rudder angle [deg]',
+            'forward speed [m/s]', 'sideways speed [m/s]', 'yaw rate [deg/sec]', 'thrust force [kN]',
+            'cross track error [m]', 'heading error [deg]', 'propeller shaft speed [rpm]']
+
+
+def log_golden(kind):
+    args = H.Args(time_step=4)
+    env, assets = (H.make_colav_iw_env(args) if kind == "colav" else H.make_rl_env(args))
+    env.reset()
+    actions = np.deg2rad(np.array([-2, 0, 5, -5, 10, 0, 0, 0, 0], dtype=np.float64))
+    for a in actions:
+        res = env.step(np.array([a], dtype=np.float64))
+        if res[-2]:
+            break
+    out = dict(meta=json.dumps(dict(kind=kind, dt=4, collav="none")), actions=actions)
+    for who, name in ((0, "test"), (1, "obs")):
+        sr = assets[who].ship_model.simulation_results
+        n = len(sr['time [s]'])
+        rows = np.unique(np.concatenate([np.arange(0, n, 7), np.arange(max(0, n - 60), n)]))
+        out[f"{name}_n"] = n
+        out[f"{name}_rows"] = rows
+        for k in LOG_KEYS:
+            if k in sr:
+                out[f"{name}|{k}"] = np.asarray(sr[k], dtype=np.float64)[rows]
+    return out
+
+
+def main_logs():
+    H.install_stubs()
+    for kind in ("colav", "rl"):
+        out = log_golden(kind)
+        np.savez_compressed(os.path.join(HERE, f"log_{kind}_dt4_kat.npz"), **out)
+        print("log", kind, out["test_n"], out["obs_n"])
+
+
 def main_sampler():
     H.install_stubs()
     for name, w in SAMPLER_POLICIES.items():
@@ -329,6 +367,9 @@ def main_sampler():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "sampler":
         main_sampler()      # only the sampler fixtures (the others are unchanged)
+    elif len(sys.argv) > 1 and sys.argv[1] == "logs":
+        main_logs()
     else:
         main()
         main_sampler()
+        main_logs()

@@ -326,7 +326,7 @@ def test_sbmpc_memory_survives_reset(kind):
     penalised against the last manoeuvre of the first.  64 environments on a collision course, an
     abandoned episode followed by a full one, each environment compared with its own oracle."""
     B = 64
-    n_first = 6 if kind == "rl" else 9      # step() calls of the first episode
+    n_first = 6 if kind == "rl" else 7      # step() calls of the first (abandoned) episode: the ships are passing each other
     args = S.get_env_args(time_step=4, collav_mode="sbmpc")
     if kind == "rl":
         assets, m = S.build_rl_assets(args)
@@ -361,7 +361,6 @@ def test_sbmpc_memory_survives_reset(kind):
                 assert sb[0, b] == oe.st.sb_p_last and sb[1, b] == oe.st.sb_chi_last
             carried = int(((sb[0] != 1.0) | (sb[1] != 0.0)).sum())
         alive = np.ones(B, dtype=bool)
-        # (rl) the first episode is abandoned after 6 step() calls, while the ships are passing each other
         for j in range(n_first if episode == 0 else 9):
             env.step(actions[:, j].cuda())
             _sync()
@@ -552,3 +551,51 @@ def test_pickle_roundtrip_rebuilds_device_state():
     r2 = env2.step(np.array([0.01]))
     assert np.array_equal(r1[0], r2[0]) and r1[1] == r2[1]
     env.close(); env2.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory log: the reference's ship_model.simulation_results
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["colav", "rl"])
+def test_trajectory_log_matches_reference_simulation_results(kind):
+    """KAT episode with the per-step log switched on: row counts equal the reference's log length after every
+    step() call, and the logged columns (states before the integration, rudder, thrust / shaft speed, e_ct,
+    heading error, repeated rows of a stopped ship) match the reference's simulation_results."""
+    g = golden(f"log_{kind}_dt4_kat")
+    ep = golden("colav_iw_dt4_kat" if kind == "colav" else "rl_dt4_kat")
+    meta = json.loads(str(g["meta"]))
+    env, assets = env_from_meta(meta, num_envs=3)
+    env.enable_trajectory_log(n_envs=2, capacity=2048)
+    env.reset()
+    for j, a in enumerate(g["actions"]):
+        res = env.step(np.full(3, a))
+        _sync()
+        assert int(env.log_count[1]) == int(ep["n_log"][j]), (j, int(env.log_count[1]), int(ep["n_log"][j]))
+        if bool(res[-2][0]):
+            break
+    for role, name in ((0, "test"), (1, "obs")):
+        sr = env.simulation_results(role, env=0)
+        assert len(sr['time [s]']) == int(g[f"{name}_n"])
+        rows = g[f"{name}_rows"]
+        for key in sr:
+            gk = f"{name}|{key}"
+            if gk not in g.files:
+                assert key == 'commanded load fraction [-]'
+                continue
+            got = np.asarray(sr[key])[rows]
+            want = g[gk]
+            scale = {'yaw rate [deg/sec]': 1e-3 * 180 / np.pi}.get(key, 1.0)
+            e = rel_err(got, want, scale)
+            assert e.max() < (1e-8 if kind == "rl" else REL_TOL), (kind, name, key, e.max(), int(e.argmax()))
+        # environment 1 logged the same episode; the whole-episode columns of the episode fixture agree row by row
+        assert np.array_equal(env.trajectory(role, env=1), env.trajectory(role, env=0))
+        assert rel_err(np.asarray(sr['north position [m]']), ep[f"{name}_log_north"], 1.0).max() < 1e-8
+        assert rel_err(np.asarray(sr['cross track error [m]']), ep[f"{name}_log_ect"], 1.0).max() < 1e-8
+    # the host mirror exposes it like the reference object does
+    assert assets[1].ship_model.simulation_results['time [s]'][:3] == [0.0, 4.0, 8.0]
+    with pytest.raises(RuntimeError):
+        env.trajectory(0, env=2)
+    env.reset()
+    _sync()
+    assert int(env.log_count[0]) == 1 and int(env.log_count[1]) == 1       # reset() starts a new log; init_step logs one row
+    env.close()

@@ -126,3 +126,15 @@ def test_event_strings_match_reference_order():
     assert E.events_to_string((1 << 5) | (1 << 7)) == ('|Ship under test reaches its final destination!|'
                                                       '|Obstacle ship reaches its final destination!|')
     assert E.EVENT_STRINGS == O.EVENT_STRINGS
+
+
+def test_layout_constants_match_header():
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "shipenv.h")).read()
+    assert int(re.search(r"#define SHIPENV_ABI_VERSION (\d+)", hdr).group(1)) == L.ABI_VERSION
+    sf = re.search(r"/\* ship_f64 rows \*/\s*enum \{(.*?)SHIPENV_SF_COUNT", hdr, re.S).group(1)
+    assert len(re.findall(r"SHIPENV_SF_\w+", sf)) == L.SF_COUNT == len(L.SF)
+    ef = re.search(r"/\* env_f64 rows \*/\s*enum \{(.*?)SHIPENV_EF_COUNT", hdr, re.S).group(1)
+    assert len(re.findall(r"SHIPENV_EF_\w+", ef)) == L.EF_COUNT == len(L.EF)
+    lg = re.search(r"SHIPENV_LOG_TIME = 0,(.*?)SHIPENV_LOG_COLS", hdr, re.S).group(1)
+    assert 1 + len(re.findall(r"SHIPENV_LOG_\w+", lg)) == len(L.LOG_COLS)
