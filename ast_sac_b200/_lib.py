@@ -78,6 +78,7 @@ EXPORTS = [
     "shipenv_construct", "shipenv_reset", "shipenv_init_step", "shipenv_step", "shipenv_substeps",
     "shipenv_ship_rollout", "shipenv_reset_host", "shipenv_step_host", "shipenv_substeps_host",
     "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math", "shipenv_set_trajectory_log",
+    "shipenv_time_env_kernel", "shipenv_env_kernel_ms",
 ]
 
 _lib = None
@@ -113,6 +114,8 @@ def load():
     L.shipenv_substeps_host.argtypes = [vp, i32, vp, vp, vp, vp]
     L.shipenv_read_counters.argtypes = [vp, vp]
     L.shipenv_set_trajectory_log.argtypes = [vp, vp, vp, i64, i64]
+    L.shipenv_time_env_kernel.argtypes = [vp, i32]
+    L.shipenv_env_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.shipenv_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.shipenv_selftest_math.argtypes = [i32, i64, C.c_uint64, vp]
     if L.shipenv_abi_version() != ABI_VERSION:

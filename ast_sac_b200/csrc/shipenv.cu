@@ -47,6 +47,12 @@ struct shipenv {
   unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch
   unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
+  // CUDA events around the env kernel itself (k_env), for shipenv_env_kernel_ms: the step() / _step() entry
+  // points also launch the prologue kernel and a memset, which a caller's own events would include
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  int time_kernels = 0;
+  double kernel_ms_sum = 0.0;                // accumulated by shipenv_env_kernel_ms
+  bool kernel_pending = false;
   int sm_count = 0;
   double* log_dev = nullptr;          // optional trajectory log (caller-owned), see shipenv_set_trajectory_log
   int32_t* log_count_dev = nullptr;
@@ -138,13 +144,28 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   }
   int persistent = h->persist_mode;
   if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
+  if (h->time_kernels) {
+    if (h->kernel_pending) {                 // fold the previous launch into the sum before reusing the events
+      float ms = 0.f;
+      if (cudaEventSynchronize(h->ev_k1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1) == cudaSuccess)
+        h->kernel_ms_sum += ms;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->queue_dev, 0, 2 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaEventRecord(h->ev_k0, st));
+  }
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
                       ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                              h->sm_count, persistent, st)
+                                              h->sm_count, persistent, h->time_kernels ? 0 : 1, st)
                       : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                                h->sm_count, persistent, st);
+                                                h->sm_count, persistent, h->time_kernels ? 0 : 1, st);
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
-  CUDA_TRY(cudaMemcpyAsync(h->done_host, h->queue_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (h->time_kernels) {
+    CUDA_TRY(cudaEventRecord(h->ev_k1, st));
+    h->kernel_pending = true;
+  }
+  // only the automatic grid policy reads the count of finished environments back
+  if (h->persist_mode < 0)
+    CUDA_TRY(cudaMemcpyAsync(h->done_host, h->queue_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   return SHIPENV_OK;
 }
 
@@ -392,6 +413,7 @@ int shipenv_destroy(shipenv_t* h) {
   cudaFree(h->mask_dev);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev_k0) { cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1); }
   for (const auto& r : h->host_regs)
     if (r.ok) cudaHostUnregister(const_cast<void*>(r.ptr));
   cudaGetLastError();   // a buffer the caller already freed / unregistered is not an error of destroy
@@ -596,6 +618,35 @@ int shipenv_set_trajectory_log(shipenv_t* h, double* log_dev, int32_t* count_dev
   }
   if (log_envs > h->num_envs) return fail(SHIPENV_E_ARG, "log_envs %lld > num_envs %lld", (long long)log_envs, h->num_envs);
   h->log_dev = log_dev; h->log_count_dev = count_dev; h->log_envs = log_envs; h->log_capacity = capacity;
+  return SHIPENV_OK;
+}
+
+int shipenv_time_env_kernel(shipenv_t* h, int enable) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (enable && !h->ev_k0) {
+    CUDA_TRY(cudaEventCreate(&h->ev_k0));
+    CUDA_TRY(cudaEventCreate(&h->ev_k1));
+  }
+  h->time_kernels = enable ? 1 : 0;
+  h->kernel_ms_sum = 0.0;
+  h->kernel_pending = false;
+  return SHIPENV_OK;
+}
+
+int shipenv_env_kernel_ms(shipenv_t* h, double* ms_out) {
+  if (!h || !ms_out) return fail(SHIPENV_E_ARG, "NULL argument");
+  if (!h->time_kernels) return fail(SHIPENV_E_STATE, "kernel timing is off (shipenv_time_env_kernel)");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->kernel_pending) {
+    float ms = 0.f;
+    CUDA_TRY(cudaEventSynchronize(h->ev_k1));
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1));
+    h->kernel_ms_sum += ms;
+    h->kernel_pending = false;
+  }
+  *ms_out = h->kernel_ms_sum;
+  h->kernel_ms_sum = 0.0;
   return SHIPENV_OK;
 }
 

@@ -493,38 +493,53 @@ __device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, dou
   const double ds_ot = d_safe + os_l / 2 + obs_l / 2;
   const double ds_min = fmin(ds_ahead, fmin(ds_behind, ds_beam)), ds_max = fmax(ds_ahead, fmax(ds_behind, ds_beam));
 
-  double sx = in.os_x, sy = in.os_y, ox = in.ob_x, oy = in.ob_y;
-  double H1 = 0.0, t = 0.0;
-#pragma unroll 1
-  for (int i = 0; i < kSbSamples; ++i) {
-    if (i > 0) {
-      sx = sx + ((i == 1) ? os_dx1 : os_dx);
-      sy = sy + ((i == 1) ? os_dy1 : os_dy);
-      ox = ox + ob_dx;
-      oy = oy + ob_dy;
-    }
-    t += kSbDt;
-    const double e0 = ox - sx, e1 = oy - sy;
+  // Beyond every safety distance a sample contributes H0 = 0 (R = C = 0), which cannot raise H1 >= 0; sqrt is
+  // monotonic, so d2 >= (largest safety distance + 1 m)^2 decides that without taking the root.
+  const double ds_far = fmax(ds_max, ds_ot) + 1.0;
+  const double far2 = fmin(ds_far * ds_far, 4.0e6);        // never beyond D_CLOSE_ either
+  double H1 = 0.0;
+  // one sample of cost_func's loop: e = obstacle - own ship, t = (i + 1) * DT_
+  auto sample = [&](double e0, double e1, double t, bool ot, double cc) {
     const double d2 = e0 * e0 + e1 * e1;
-    if (!(d2 < 4.1e6)) continue;            // certainly dist >= D_CLOSE_: R = C = 0, H0 = 0 cannot raise H1
+    if (!(d2 < far2)) return;
     const double dist = sqrt(d2);
-    if (!(dist < d_close)) continue;
-    const bool ot = (i == 0) ? otA : otB;
+    if (!(dist < d_close)) return;
     bool within;
     if (ot) within = dist < ds_ot;
-    else if (dist < ds_min) within = true;  // inside every sector's safety distance
+    else if (dist < ds_min) within = true;                   // inside every sector's safety distance
     else if (!(dist < ds_max)) within = false;
     else {
+#if SENV_FAST_MATH
+      // phi_o = wrap(atan2(-e1, -e0) - psi_o + pi/2) in [-pi, pi): cos(phi_o) = (e1 co - e0 so) / dist,
+      // sin(phi_o) = -(e0 co + e1 so) / dist, so phi_o > PHI  <=>  sin(phi_o) > 0 and cos(phi_o) < cos(PHI)
+      // (PHI = 68.5 deg lies in (0, pi)); phi_o == PHI has measure zero and falls to the "ahead" distance like
+      // every phi_o < PHI.  Same decision as the atan2 form up to the rounding of either.
+      const double xc = e1 * co - e0 * so, ys = -(e0 * co + e1 * so);
+      const bool behind = (ys > 0.0) && (xc < 0.3665012267242973 * dist);       // cos(np.deg2rad(68.5))
+      within = dist < (behind ? ds_behind : ds_ahead);
+#else
       const double phi_o = wrap_pmpi(atan2(-e1, -e0) - in.ob_psi + kPi / 2);
       const double d_safe_i = (phi_o < PHI) ? ds_ahead : ((phi_o > PHI) ? ds_behind : ds_beam);
       within = dist < d_safe_i;
+#endif
     }
     if (within) {
       const double q = d_safe / dist;
       const double R = (1.0 / t) * ((q * q) * (q * q));     // (1 / |t - t0| ** P_) * (d_safe / dist) ** Q_
-      const double H0 = ((i == 0) ? ccA : ccB) * R + 0.0;   // + KAPPA_ * mu, KAPPA_ = 0
+      const double H0 = cc * R + 0.0;                       // + KAPPA_ * mu, KAPPA_ = 0
       if (H0 > H1) H1 = H0;
     }
+  };
+  double sx = in.os_x, sy = in.os_y, ox = in.ob_x, oy = in.ob_y;
+  sample(ox - sx, oy - sy, kSbDt, otA, ccA);                                   // i = 0: measured state
+  sx = sx + os_dx1; sy = sy + os_dy1; ox = ox + ob_dx; oy = oy + ob_dy;
+  sample(ox - sx, oy - sy, 2 * kSbDt, otB, ccB);                               // i = 1
+  double t = 2 * kSbDt;
+#pragma unroll 2
+  for (int i = 2; i < kSbSamples; ++i) {
+    sx = sx + os_dx; sy = sy + os_dy; ox = ox + ob_dx; oy = oy + ob_dy;
+    t += kSbDt;
+    sample(ox - sx, oy - sy, t, otB, ccB);
   }
   const double d_chi = chi_ca - in.chi_last;                // delta_Chi, sbmpc.py:303-310
   double dl_chi = 0.0;
@@ -1001,39 +1016,45 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       // the LOS integrator advances a first time here (quirk 2 of SURVEY.md section 8)
       if (caller) in.chi_d = -los_guidance(P, s);
       const double q_east = shfl_xor_f64(s.east, 1), q_north = shfl_xor_f64(s.north, 1);
-      const double q_yaw = shfl_xor_f64(s.yaw, 1), q_u = shfl_xor_f64(s.u, 1), q_v = shfl_xor_f64(s.v, 1);
       // own ship = assets[0] (ship under test), obstacle = assets[1], whichever asset calls
-      in.os_x = role == 0 ? s.east : q_east; in.os_y = role == 0 ? s.north : q_north; in.os_v = role == 0 ? s.v : q_v;
+      in.os_x = role == 0 ? s.east : q_east; in.os_y = role == 0 ? s.north : q_north;
       in.ob_x = role == 1 ? s.east : q_east; in.ob_y = role == 1 ? s.north : q_north;
-      in.ob_psi = -(role == 1 ? s.yaw : q_yaw);
-      in.ob_u = role == 1 ? s.u : q_u; in.ob_v = role == 1 ? s.v : q_v;
-      in.u_d = P.desired_speed;
-      in.chi_last = sb_chi_last; in.p_last = sb_p_last;
+      // D_INIT_ test (sbmpc.py:154-166); both lanes of the pair see the same two positions, so the lane that
+      // does not call resets its copy of the SBMPC memory alongside the caller
+      const bool pair_calls = __shfl_sync(FULL_MASK, (int)caller, (lane & ~1) | caller_role) != 0;
       bool active = false;
-      if (caller) {
+      if (pair_calls) {
         const double d0 = in.ob_x - in.os_x, d1 = in.ob_y - in.os_y;
-        active = sqrt(d0 * d0 + d1 * d1) < 2000.0;            // D_INIT_, sbmpc.py:154-166
+        active = sqrt(d0 * d0 + d1 * d1) < 2000.0;
         if (!active) { sb_p_last = 1.0; sb_chi_last = 0.0; }
       }
       unsigned todo = __ballot_sync(FULL_MASK, caller && active);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int best = sbmpc_warp_argmin(in, src, lane, G.ship[1].l_ship, G.ship[1].w_ship);
-        if (lane == src) {
-          double u_best = 1.0, chi_best = 0.0;
-          if (best >= 0) {
-            const int ic = best >> 2, jp = best & 3;
-            chi_best = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);
-            u_best = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
+      if (todo) {                                                // warp-uniform: most steps have no active pair
+        const double q_yaw = shfl_xor_f64(s.yaw, 1), q_u = shfl_xor_f64(s.u, 1), q_v = shfl_xor_f64(s.v, 1);
+        in.os_v = role == 0 ? s.v : q_v;
+        in.ob_psi = -(role == 1 ? s.yaw : q_yaw);
+        in.ob_u = role == 1 ? s.u : q_u; in.ob_v = role == 1 ? s.v : q_v;
+        in.u_d = P.desired_speed;
+        in.chi_last = sb_chi_last; in.p_last = sb_p_last;
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int best = sbmpc_warp_argmin(in, src, lane, G.ship[1].l_ship, G.ship[1].w_ship);
+          if (lane == src) {
+            double u_best = 1.0, chi_best = 0.0;
+            if (best >= 0) {
+              const int ic = best >> 2, jp = best & 3;
+              chi_best = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);
+              u_best = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
+            }
+            sb_p_last = u_best; sb_chi_last = chi_best;
+            speed_factor = u_best; heading_offset = -chi_best;
           }
-          sb_p_last = u_best; sb_chi_last = chi_best;
-          speed_factor = u_best; heading_offset = -chi_best;
         }
+        // the pair shares one SBMPC object: the other lane takes over the caller's copy of its memory
+        sb_p_last = __shfl_sync(FULL_MASK, sb_p_last, (lane & ~1) | caller_role);
+        sb_chi_last = __shfl_sync(FULL_MASK, sb_chi_last, (lane & ~1) | caller_role);
       }
-      // the pair shares one SBMPC object: the other lane takes over the caller's copy of its memory
-      sb_p_last = __shfl_sync(FULL_MASK, sb_p_last, (lane & ~1) | caller_role);
-      sb_chi_last = __shfl_sync(FULL_MASK, sb_chi_last, (lane & ~1) | caller_role);
     }
     if (stepping) {
       const double dt = P.dt;
@@ -1399,11 +1420,13 @@ cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actio
 }
 
 cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,
-                       unsigned long long* queue, int sm_count, int persistent, cudaStream_t st) {
+                       unsigned long long* queue, int sm_count, int persistent, int clear_queue, cudaStream_t st) {
   // queue[0] = work-queue counter, queue[1] = environments found already done by this launch; both
   // restart at 0 for every launch (ordered on the same stream)
-  cudaError_t e = cudaMemsetAsync(queue, 0, 2 * sizeof(unsigned long long), st);
-  if (e != cudaSuccess) return e;
+  if (clear_queue) {
+    cudaError_t e = cudaMemsetAsync(queue, 0, 2 * sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+  }
   if (model == SHIPENV_MODEL_SIMPLE) {
     if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
     else launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);

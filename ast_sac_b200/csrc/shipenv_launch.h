@@ -41,7 +41,8 @@ struct SenvView {
   cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st);                                            \
   cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, cudaStream_t st);        \
   cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,   \
-                         unsigned long long* queue, int sm_count, int persistent, cudaStream_t st);            \
+                         unsigned long long* queue, int sm_count, int persistent, int clear_queue,           \
+                         cudaStream_t st);                                                                     \
   cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st);                            \
   cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned long long* mismatches_dev,   \
                                    cudaStream_t st);                                                           \

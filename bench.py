@@ -40,7 +40,10 @@ N_RL_STEPS = 9
 #    ncu capture under profiles/ (includes the CUDA math library's sin/cos/atan2/exp internals and
 #    the map-geometry tests); filled in from profiles/r01_ncu_summary.md.
 FLOP_ALGO = {"colav_iw": 370.0 + 26.0, "rl": 450.0 + 31.0}
-FLOP_EXEC = {"colav_iw": 599.0, "rl": 1150.0}     # profiles/r01_ncu_summary.md section 2 (fast build)
+FLOP_EXEC = {"colav_iw": 594.0, "rl": 1170.0}     # profiles/r01_ncu_summary.md part 2, section 2 (fast build)
+# DRAM bytes (read + written) of one k_env<MODE_STEP> launch over 1e5 environments, from the ncu --set full
+# capture summarised in profiles/r01_ncu_summary.md part 2 (dram__bytes_read.sum + dram__bytes_write.sum)
+TRAFFIC_PER_LAUNCH_1E5 = {"colav_iw": 37.8e6, "rl": 37.7e6}
 # HBM bytes per env-step when every simulator step is its own launch (K = 1): DESIGN.md section 4
 BYTES_K1 = 2 * 2 * (17 * 8 + 4) + 2 * (5 * 8 + 2 * 4) + 32 + 8 + 4 + 4     # ship rows r+w, env rows r+w, outputs = 704 B (ABI v5)
 
@@ -264,9 +267,12 @@ def run_b200(a, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     sampler.start()
     c0 = env.total_substeps()
-    step_ms, launch_ms = [], []
+    step_ms, launch_ms, kernel_ms = [], [], []
+    lib = L.load()
+    L.check(lib.shipenv_time_env_kernel(env._handle, 1))   # CUDA events around k_env itself, on its own stream
     barrier()
     t_wall0 = time.perf_counter()
+    import ctypes
     for _ in range(a.steps):
         l2_flush.fill_(1.0)                      # > 126 MB L2: evict the state between timed iterations
         pairs = one_episode(events=True)
@@ -274,25 +280,32 @@ def run_b200(a, rank, local_rank, world):
         ms = [s.elapsed_time(e) for s, e in pairs]
         launch_ms.append(ms)
         step_ms.append(sum(ms))
+        kms = ctypes.c_double()
+        L.check(lib.shipenv_env_kernel_ms(env._handle, ctypes.byref(kms)))
+        kernel_ms.append(kms.value)
     barrier()
+    L.check(lib.shipenv_time_env_kernel(env._handle, 0))
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     steps_done = env.total_substeps() - c0
     local_time_s = sum(step_ms) / 1e3
 
     # ---- per-launch roofline of the dominant kernel (k_env<.., MODE_STEP>): the 9 step() launches
-    launch_ms = np.array(launch_ms)                       # [K, 10]
-    step_kernel_ms = launch_ms[:, 1:].sum(axis=1)         # the 9 step() launches of each episode
+    launch_ms = np.array(launch_ms)                       # [K, 10]: reset() + 9 step() calls (prologue + k_env each)
+    step_kernel_ms = np.array(kernel_ms)                  # the 9 k_env launches of each episode, device time
     env_steps_per_episode = steps_done / a.steps
     flops_exec = FLOP_EXEC[a.workload] * env_steps_per_episode
     achieved_tf = flops_exec / (step_kernel_ms.mean() * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": "k_env<MODE_STEP> (9 launches per episode)",
+        "ms_per_launch": float(step_kernel_ms.mean() / N_RL_STEPS),
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
         "peak_source": "DFMA microbenchmark measured live in this run (MEASURED_PEAKS.json has no FP64 entry)",
         "flop_per_env_step_executed": FLOP_EXEC[a.workload], "flop_per_env_step_algorithmic": FLOP_ALGO[a.workload],
         "achieved_algorithmic": FLOP_ALGO[a.workload] * env_steps_per_episode / (step_kernel_ms.mean() * 1e-3) / 1e12,
-        "traffic": None,
+        "traffic": TRAFFIC_PER_LAUNCH_1E5[a.workload] if (B == 100_000 and a.collav == "none") else None,
+        "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/)",
+        "algorithmic_bytes_per_launch": float(B * (2 * (17 * 8 + 4) * 2 + 2 * (5 * 8 + 8) + 48)),
         "share_of_step": float(step_kernel_ms.sum() / launch_ms.sum()),
     }
 
