@@ -13,9 +13,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 5
+ABI_VERSION = 6
 MATH_STRICT, MATH_FAST = 0, 1
-MODEL_SIMPLE, MODEL_DETAILED = 0, 1
+MODEL_SIMPLE, MODEL_DETAILED, MODEL_SIMPLIFIED = 0, 1, 2
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
 COLLAV_NONE, COLLAV_SIMPLE, COLLAV_SBMPC = 0, 1, 2
 
@@ -42,7 +42,7 @@ SHIP_PARAM_DOUBLES = [
     "kp_ship_speed", "ki_ship_speed", "kp_shaft_speed", "ki_shaft_speed", "max_shaft_speed", "init_shaft_err_i",
     "ctrl_dt", "inv_ctrl_dt", "hdg_kp", "hdg_kd", "hdg_ki", "max_rudder", "los_ra", "los_r", "los_ki", "los_limit",
     "desired_speed", "p_me", "p_el", "tq_me_max", "tq_el_max", "d_me", "d_hsg", "r_me", "r_hsg", "jp",
-    "k_torque", "thrust_coeff", "nav_fail_tol",
+    "k_torque", "thrust_coeff", "k_thrust", "thrust_tau", "nav_fail_tol",
 ]
 
 

@@ -95,11 +95,13 @@ int validate(const ShipEnvParams* p, long long num_envs) {
     return fail(SHIPENV_E_ARG, "both ships of an environment must use the same ship model class");
   for (int s = 0; s < 2; ++s) {
     const ShipEnvShipParams& q = p->ship[s];
-    if (q.model_kind != SHIPENV_MODEL_SIMPLE && q.model_kind != SHIPENV_MODEL_DETAILED)
+    if (q.model_kind < SHIPENV_MODEL_SIMPLE || q.model_kind > SHIPENV_MODEL_SIMPLIFIED)
       return fail(SHIPENV_E_ARG, "ship[%d].model_kind invalid", s);
+    if (q.model_kind == SHIPENV_MODEL_SIMPLIFIED && !(q.thrust_tau > 0.0))
+      return fail(SHIPENV_E_ARG, "ship[%d].thrust_tau must be positive", s);
     if (q.n_wp < 2 || q.n_wp > SHIPENV_MAX_WP) return fail(SHIPENV_E_ARG, "ship[%d].n_wp must be in [2, %d]", s, SHIPENV_MAX_WP);
     if (!(q.dt > 0.0) || !(q.ctrl_dt > 0.0)) return fail(SHIPENV_E_ARG, "ship[%d] time steps must be positive", s);
-    if (q.model_kind == SHIPENV_MODEL_DETAILED && !(q.dt_shaft > 0.0))
+    if (q.model_kind != SHIPENV_MODEL_SIMPLE && !(q.dt_shaft > 0.0))
       return fail(SHIPENV_E_ARG, "ship[%d].dt_shaft must be positive", s);
   }
   if (p->env_kind != SHIPENV_ENV_COLAV_NONIW && p->ship[1].n_wp + p->max_sampling_frequency > 255)

@@ -166,6 +166,12 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     s.spd_err_i = error_i;
     const double out = error * P.spd_kp + d_error * P.spd_kd + error_i * P.spd_ki;
     cmd = sat(out, -P.max_thrust, P.max_thrust);
+  } else if (MODEL == SHIPENV_MODEL_SIMPLIFIED) {
+    // ThrottleFromSpeedSetPointSimplifiedPropulsion.throttle (rl_env controllers.py:229-232)
+    const double error = speed_set_point - s.u;
+    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    s.spd_err_i = error_i;
+    cmd = sat(error * P.kp_ship_speed + error_i * P.ki_ship_speed, 0.0, 1.1);
   } else {
     const double error = speed_set_point - s.u;
     const double error_i = s.spd_err_i + error * P.ctrl_dt;
@@ -202,6 +208,12 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   double thrust, d_omega = 0.0;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
     thrust = cmd;
+  } else if (MODEL == SHIPENV_MODEL_SIMPLIFIED) {
+    // SimplifiedMachineryModel.update_thrust_force (ship_engine.py:508-513); the thrust state feeds the
+    // kinetics before it is integrated
+    const double power = cmd * (P.p_me + P.p_el);
+    thrust = s.omega;
+    d_omega = (-P.k_thrust * s.omega + power) / P.thrust_tau;
   } else {
     const double w = s.omega;
     // (the divisions stay exact in both builds: replacing them by reciprocal multiplications moved the
@@ -278,7 +290,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   s.u = s.u + d_u * dt;
   s.v = s.v + d_v * dt;
   s.r = s.r + d_r * dt;
-  if (MODEL == SHIPENV_MODEL_DETAILED) s.omega = s.omega + d_omega * P.dt_shaft;
+  if (MODEL != SHIPENV_MODEL_SIMPLE) s.omega = s.omega + d_omega * P.dt_shaft;
   s.time = s.time + dt;
 }
 
@@ -1360,8 +1372,10 @@ cudaError_t launch_reset(const SenvView& v, int model, const uint8_t* mask, cons
                          int reinit, cudaStream_t st) {
   if (model == SHIPENV_MODEL_SIMPLE)
     k_reset<SHIPENV_MODEL_SIMPLE><<<ship_grid(v), kBlock, 0, st>>>(v, mask, init, do_init, reinit);
-  else
+  else if (model == SHIPENV_MODEL_DETAILED)
     k_reset<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, mask, init, do_init, reinit);
+  else
+    k_reset<SHIPENV_MODEL_SIMPLIFIED><<<ship_grid(v), kBlock, 0, st>>>(v, mask, init, do_init, reinit);
   return cudaGetLastError();
 }
 
@@ -1430,9 +1444,12 @@ cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, con
   if (model == SHIPENV_MODEL_SIMPLE) {
     if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
     else launch_env_kind<SHIPENV_MODEL_SIMPLE, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
-  } else {
+  } else if (model == SHIPENV_MODEL_DETAILED) {
     if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
     else launch_env_kind<SHIPENV_MODEL_DETAILED, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
+  } else {
+    if (mode == MODE_STEP) launch_env_kind<SHIPENV_MODEL_SIMPLIFIED, MODE_STEP>(v, env_kind, actions, k, queue, sm_count, persistent, st);
+    else launch_env_kind<SHIPENV_MODEL_SIMPLIFIED, MODE_SUBSTEPS>(v, env_kind, actions, k, queue, sm_count, persistent, st);
   }
   return cudaGetLastError();
 }
@@ -1445,7 +1462,8 @@ cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned 
 
 cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st) {
   if (model == SHIPENV_MODEL_SIMPLE) k_ship_rollout<SHIPENV_MODEL_SIMPLE><<<ship_grid(v), kBlock, 0, st>>>(v, k);
-  else k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, k);
+  else if (model == SHIPENV_MODEL_DETAILED) k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, k);
+  else k_ship_rollout<SHIPENV_MODEL_SIMPLIFIED><<<ship_grid(v), kBlock, 0, st>>>(v, k);
   return cudaGetLastError();
 }
 

@@ -115,7 +115,23 @@ def pack_ship_params(asset: ShipAssets, nav_fail_tol: float, dt_shaft: Optional[
         p.wp_north[i] = float(nav.north[i])
         p.wp_east[i] = float(nav.east[i])
     p.n_wp = n_wp
-    if hasattr(sm, "ship_machinery_model"):
+    if hasattr(sm, "ship_machinery_model") and hasattr(sm.ship_machinery_model, "thrust_time_constant"):
+        # hull + SimplifiedMachineryModel (thrust-force state), ship_engine.py:484-519
+        mm = sm.ship_machinery_model
+        tc = asset.throttle_controller
+        if tc is None or not hasattr(tc, "ship_speed_controller") or hasattr(tc, "shaft_speed_controller"):
+            raise ValueError("ShipModelSimplifiedPropulsion assets need a ThrottleFromSpeedSetPointSimplifiedPropulsion")
+        p.model_kind = L.MODEL_SIMPLIFIED
+        p.c_rudder_v, p.c_rudder_r = mm.c_rudder_v, mm.c_rudder_r
+        p.init_omega = mm.thrust                       # the machinery state row holds the thrust force
+        p.dt_shaft = mm.int.dt        # (the reference defines no reset() for this machinery model: no dt quirk)
+        p.kp_ship_speed, p.ki_ship_speed = tc.ship_speed_controller.kp, tc.ship_speed_controller.ki
+        if tc.ship_speed_controller.time_step != pid.time_step:
+            raise ValueError("all controllers of an asset must share one time_step")
+        p.p_me = mm.mode.available_propulsion_power_main_engine
+        p.p_el = mm.mode.available_propulsion_power_electrical
+        p.k_thrust, p.thrust_tau = mm.k_thrust, mm.thrust_time_constant
+    elif hasattr(sm, "ship_machinery_model"):
         mm = sm.ship_machinery_model
         tc = asset.throttle_controller
         if tc is None:
@@ -465,6 +481,9 @@ class BatchedShipEnv:
             out['propeller shaft speed [rpm]'] = c["omega"] * 30 / np.pi
             out['commanded load fraction [-]'] = c["cmd"]
             out['thrust force [kN]'] = p.thrust_coeff * c["omega"] * np.abs(c["omega"]) / 1000      # ship_engine.py:411-414
+        elif p.model_kind == L.MODEL_SIMPLIFIED:
+            out['commanded load fraction [-]'] = c["cmd"]
+            out['thrust force [kN]'] = c["omega"] / 1000          # the machinery state row is the thrust force [N]
         else:
             out['thrust force [kN]'] = c["cmd"]          # the reference logs newtons under this key (ship_model.py:427)
         out['cross track error [m]'] = c["e_ct"]

@@ -166,6 +166,34 @@ def build_colav_assets(args, iw=True, test_init=None, obs_init=None, sim_time=10
     return [test, obs], PolygonObstacle(MAP_DATA)
 
 
+def build_simplified_assets(args, sim_time=10000, thrust_force_dynamic_time_constant=30.0, initial_thrust_force=0.0,
+                            kp=3.0, ki=0.02):
+    """The run/env_setup.py pair with the hull driven by SimplifiedMachineryModel (thrust-force state T) and
+    ThrottleFromSpeedSetPointSimplifiedPropulsion instead of the detailed machinery (A8' of SURVEY.md section 8a;
+    numbers of tests/golden/make_golden.py:SIMPLIFIED)."""
+    from .sim.controllers import ThrottleFromSpeedSetPointSimplifiedPropulsion
+    from .sim.ship_engine import SimplifiedPropulsionMachinerySystemConfiguration
+    from .sim.ship_model import ShipModelSimplifiedPropulsion
+    assets, m = build_rl_assets(args, sim_time=sim_time)
+    out = []
+    for a in assets:
+        full = a.ship_model.ship_machinery_model
+        cfg = SimplifiedPropulsionMachinerySystemConfiguration(
+            hotel_load=full.hotel_load, machinery_modes=full.machinery_modes, machinery_operating_mode=0,
+            specific_fuel_consumption_coefficients_me=None, specific_fuel_consumption_coefficients_dg=None,
+            thrust_force_dynamic_time_constant=thrust_force_dynamic_time_constant,
+            rudder_angle_to_sway_force_coefficient=full.c_rudder_v, rudder_angle_to_yaw_force_coefficient=full.c_rudder_r,
+            max_rudder_angle_degrees=30)
+        sm = a.ship_model
+        model = ShipModelSimplifiedPropulsion(ship_config=sm.ship_config, simulation_config=sm.simulation_config,
+                                              environment_config=sm.environment_config, machinery_config=cfg,
+                                              initial_thrust_force=initial_thrust_force)
+        out.append(ShipAssets(ship_model=model, auto_pilot=a.auto_pilot, desired_forward_speed=a.desired_forward_speed,
+                              integrator_term=[], time_list=[], type_tag=a.type_tag, stop_flag=False,
+                              throttle_controller=ThrottleFromSpeedSetPointSimplifiedPropulsion(kp=kp, ki=ki, time_step=args.time_step)))
+    return out, m
+
+
 def prepare_multiship_rl_env(args, num_envs=1, device=None, mode="PTI", init_states=None, math_mode=None, **kw):
     """Drop-in for run/env_setup.py:prepare_multiship_rl_env -> (env, assets)."""
     assets, map_obj = build_rl_assets(args, mode=mode, **kw)

@@ -64,6 +64,13 @@ class EngineThrottleFromSpeedSetPoint:
         self.max_shaft_speed = max_shaft_speed
 
 
+class ThrottleFromSpeedSetPointSimplifiedPropulsion:
+    """rl_env controllers.py:212-232: PI on the ship speed -> throttle in [0, 1.1]."""
+
+    def __init__(self, kp: float, ki: float, time_step: float):
+        self.ship_speed_controller = PiController(kp=kp, ki=ki, time_step=time_step)
+
+
 class HeadingByReferenceController:
     def __init__(self, gains: HeadingControllerGains, time_step, max_rudder_angle):
         self.gains = gains

@@ -126,3 +126,37 @@ class ShipMachineryModel:
         self.time_step = time_step
         self.int = _Integrator(dt=time_step)
         self._initial_parameters = {'omega': self.omega}
+
+
+class SimplifiedPropulsionMachinerySystemConfiguration(NamedTuple):   # ship_engine.py:148-157
+    hotel_load: float
+    machinery_modes: MachineryModes
+    machinery_operating_mode: int
+    specific_fuel_consumption_coefficients_me: FuelConsumptionCoefficients
+    specific_fuel_consumption_coefficients_dg: FuelConsumptionCoefficients
+    thrust_force_dynamic_time_constant: float
+    rudder_angle_to_sway_force_coefficient: float
+    rudder_angle_to_yaw_force_coefficient: float
+    max_rudder_angle_degrees: float
+
+
+class SimplifiedMachineryModel:
+    """Parameter holder with the attribute names of SimplifiedMachineryModel (ship_engine.py:484-519): first-order
+    thrust-force dynamics  dT/dt = (-k_thrust * T + load * available_power) / time_constant."""
+
+    def __init__(self, machinery_config: SimplifiedPropulsionMachinerySystemConfiguration, time_step: float,
+                 initial_thrust_force: float):
+        self.machinery_modes = machinery_config.machinery_modes
+        self.hotel_load = machinery_config.hotel_load
+        for mode in self.machinery_modes.list_of_modes:
+            mode.update_available_propulsion_power(self.hotel_load)
+        self.mode = self.machinery_modes.list_of_modes[machinery_config.machinery_operating_mode]
+        self.c_rudder_v = machinery_config.rudder_angle_to_sway_force_coefficient
+        self.c_rudder_r = machinery_config.rudder_angle_to_yaw_force_coefficient
+        self.rudder_ang_max = machinery_config.max_rudder_angle_degrees * np.pi / 180
+        self.thrust = initial_thrust_force
+        self.d_thrust = 0
+        self.k_thrust = 2160 / 790
+        self.thrust_time_constant = machinery_config.thrust_force_dynamic_time_constant
+        self.time_step = time_step
+        self.int = _Integrator(dt=time_step)

@@ -141,4 +141,19 @@ class ShipModelAST(BaseShipModel):
             time_step=self.int.dt)
 
 
+class ShipModelSimplifiedPropulsion(BaseShipModel):
+    """Hull driven by SimplifiedMachineryModel (thrust-force state T).  The reference ships the machinery model
+    (ship_engine.py:484-519) and its throttle controller (rl_env controllers.py:212-232) but no ship model class
+    that uses them; this one wires them the way ShipModelAST wires the detailed machinery
+    (rl_env ship_model.py:882-901): the current thrust state feeds the kinetics, then hull and thrust state are
+    integrated."""
+
+    def __init__(self, ship_config: ShipConfiguration, simulation_config: SimulationConfiguration,
+                 environment_config: EnvironmentConfiguration, machinery_config, initial_thrust_force: float = 0.0):
+        super().__init__(ship_config, simulation_config, environment_config)
+        from .ship_engine import SimplifiedMachineryModel
+        self.ship_machinery_model = SimplifiedMachineryModel(machinery_config=machinery_config, time_step=self.int.dt,
+                                                             initial_thrust_force=initial_thrust_force)
+
+
 ShipModel = ShipModelAST      # identical dynamics (rl_env ship_model.py:664 vs :803); only the log keys differ

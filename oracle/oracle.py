@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 MAX_WP, MAX_POLY, MAX_VERT = 32, 16, 128
-MODEL_SIMPLE, MODEL_DETAILED = 0, 1
+MODEL_SIMPLE, MODEL_DETAILED, MODEL_SIMPLIFIED = 0, 1, 2
 HSG = {"MOTOR": 0, "GEN": 1, "OFF": 2}
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
 COLLAV = {"none": 0, None: 0, "simple": 1, "sbmpc": 2}
@@ -73,6 +73,10 @@ class ShipConfig(C.Structure):
     _fields_ = [(n, _D) for n in _SHIP_DOUBLES] + [
         ("wp_north", _D * MAX_WP), ("wp_east", _D * MAX_WP),
         ("n_wp", C.c_int32), ("model_kind", C.c_int32), ("shaft_generator_state", C.c_int32), ("pad_", C.c_int32)]
+
+
+class SimplifiedMachinery(C.Structure):
+    _fields_ = [("thrust_force_dynamic_time_constant", _D), ("initial_thrust_force", _D)]
 
 
 class Map(C.Structure):
@@ -142,6 +146,8 @@ def lib():
         L.orc_env_step.argtypes = [C.POINTER(EnvConfig), C.POINTER(EnvState), _D, C.POINTER(StepResult)]
         L.orc_ship_rollout.argtypes = [C.POINTER(ShipConfig), C.POINTER(ShipState), C.c_int64, C.c_int,
                                        C.c_void_p, C.c_void_p]
+        L.orc_simplified_rollout.argtypes = [C.POINTER(ShipConfig), C.POINTER(SimplifiedMachinery), C.POINTER(ShipState),
+                                             C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_bench_episodes.restype = C.c_int64
         L.orc_bench_episodes.argtypes = [C.POINTER(EnvConfig), C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p, C.c_void_p]
@@ -238,6 +244,23 @@ def ship_rollout(cfg: ShipConfig, n_steps: int, record_every: int = 1):
     out = np.zeros((n_rec, 8), dtype=np.float64)
     wpt = np.zeros((n_rec,), dtype=np.int32)
     lib().orc_ship_rollout(C.byref(cfg), C.byref(st), n_steps, record_every, out.ctypes.data, wpt.ctypes.data)
+    return out, wpt, st
+
+
+def simplified_rollout(cfg: ShipConfig, thrust_time_constant: float, initial_thrust: float, n_steps: int,
+                       record_every: int = 1):
+    """Bare loop of a hull driven by SimplifiedMachineryModel (cfg.model_kind == MODEL_SIMPLIFIED); the omega
+    column of the returned states holds the thrust-force state."""
+    assert cfg.model_kind == MODEL_SIMPLIFIED
+    st = ShipState()
+    lib().orc_ship_init(C.byref(cfg), C.byref(st))
+    st.omega = initial_thrust                       # self.thrust = initial_thrust_force, ship_engine.py:504
+    m = SimplifiedMachinery(thrust_time_constant, initial_thrust)
+    n_rec = n_steps // record_every
+    out = np.zeros((n_rec, 8), dtype=np.float64)
+    wpt = np.zeros((n_rec,), dtype=np.int32)
+    lib().orc_simplified_rollout(C.byref(cfg), C.byref(m), C.byref(st), n_steps, record_every, out.ctypes.data,
+                                 wpt.ctypes.data)
     return out, wpt, st
 
 

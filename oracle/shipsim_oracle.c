@@ -153,6 +153,11 @@ static double autopilot_rudder(const OrcShipConfig* c, OrcShipState* s, double h
  * EngineThrottleFromSpeedSetPoint.throttle (rl_env controllers.py:185-189) with
  * measured_shaft_speed = forward_speed (rl_env env.py:322-326,397-401,494-498). */
 static double speed_command(const OrcShipConfig* c, OrcShipState* s, double set_point) {
+  if (c->model_kind == ORC_MODEL_SIMPLIFIED) {
+    /* ThrottleFromSpeedSetPointSimplifiedPropulsion.throttle, rl_env controllers.py:212-232 */
+    double thr = pi_ctrl(c->kp_ship_speed, c->ki_ship_speed, c->ctrl_time_step, &s->spd_err_i, set_point, s->u);
+    return sat(thr, 0, 1.1);
+  }
   if (c->model_kind == ORC_MODEL_SIMPLE) {
     double out = pid_ctrl(c->spd_kp, c->spd_kd, c->spd_ki, c->ctrl_time_step, &s->spd_err_i, &s->spd_prev_err,
                           set_point, s->u);
@@ -167,6 +172,8 @@ static double speed_command(const OrcShipConfig* c, OrcShipState* s, double set_
 /* update_differentials + integrate_differentials + int.next_time:
  * SimpleShipModel ship_model.py:351-416; ShipModelAST rl_env ship_model.py:834-901;
  * ShipMachineryModel ship_engine.py:403-443; EulerInt utils.py:42-53. */
+static const OrcSimplifiedMachinery* g_simplified = NULL;   /* set by orc_simplified_rollout only */
+
 static void ship_dynamics(const OrcShipConfig* c, const Derived* d, OrcShipState* s, double command,
                           double rudder_angle) {
   const double dt = c->integration_step;
@@ -180,6 +187,13 @@ static void ship_dynamics(const OrcShipConfig* c, const Derived* d, OrcShipState
   double thrust, d_omega = 0.0;
   if (c->model_kind == ORC_MODEL_SIMPLE) {
     thrust = command;
+  } else if (c->model_kind == ORC_MODEL_SIMPLIFIED) {
+    /* SimplifiedMachineryModel.update_thrust_force, ship_engine.py:508-513; the machinery state (thrust
+     * force, in s->omega's slot) feeds the kinetics before it is integrated, like ShipModelAST's shaft speed
+     * (rl_env ship_model.py:882-901) */
+    double power = command * (d->p_me + d->p_el);
+    thrust = s->omega;
+    d_omega = (-(2160.0 / 790.0) * s->omega + power) / g_simplified->thrust_force_dynamic_time_constant;
   } else {
     double w = s->omega;
     double a_me = command * d->p_me / (w + 0.1);
@@ -237,7 +251,7 @@ static void ship_dynamics(const OrcShipConfig* c, const Derived* d, OrcShipState
   s->u = s->u + d_u * dt;
   s->v = s->v + d_v * dt;
   s->r = s->r + d_r * dt;
-  if (c->model_kind == ORC_MODEL_DETAILED) s->omega = s->omega + d_omega * c->dt_shaft;
+  if (c->model_kind != ORC_MODEL_SIMPLE) s->omega = s->omega + d_omega * c->dt_shaft;
   s->time = s->time + dt;                                       /* next_time, utils.py:42-48 */
   s->last_rudder = rudder_angle;
   s->last_thrust = command;
@@ -249,6 +263,14 @@ static void log_row(OrcShipState* s) {
   s->log_north = s->north; s->log_east = s->east;
   s->log_e_ct = s->e_ct;
   s->n_log += 1;
+}
+
+void orc_simplified_rollout(const OrcShipConfig* c, const OrcSimplifiedMachinery* m, OrcShipState* s, int64_t n_steps,
+                            int record_every, double* out_states, int32_t* out_wpt) {
+  /* bare loop of a hull driven by SimplifiedMachineryModel (A8' of SURVEY.md section 8a); not re-entrant */
+  g_simplified = m;
+  orc_ship_rollout(c, s, n_steps, record_every, out_states, out_wpt);
+  g_simplified = NULL;
 }
 
 void orc_ship_rollout(const OrcShipConfig* c, OrcShipState* s, int64_t n_steps, int record_every,

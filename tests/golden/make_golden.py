@@ -348,6 +348,83 @@ def log_golden(kind):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# A8' of SURVEY.md section 8a: SimplifiedMachineryModel (thrust-force state T).  No ship model class of the
+# reference consumes it, so the golden composes the reference's OWN pieces the way ShipModelAST composes the
+# detailed machinery (rl_env ship_model.py:882-901): the hull of a ShipModelAST instance whose
+# ship_machinery_model is replaced by an adapter around the reference's SimplifiedMachineryModel, driven by the
+# reference's ThrottleFromSpeedSetPointSimplifiedPropulsion and HeadingBySampledRouteController.
+# ------------------------------------------------------------------------------------------------
+SIMPLIFIED = dict(thrust_force_dynamic_time_constant=30.0, initial_thrust_force=0.0, kp=3.0, ki=0.02)
+
+
+def bare_simplified(dt, n_steps):
+    from rl_env.ship_in_transit.sub_systems.ship_engine import (SimplifiedMachineryModel,
+                                                               SimplifiedPropulsionMachinerySystemConfiguration)
+    from rl_env.ship_in_transit.sub_systems.controllers import ThrottleFromSpeedSetPointSimplifiedPropulsion
+    args = H.Args(time_step=dt)
+    assets, _ = H.build_rl_assets(args, mode="PTI")
+    a = assets[0]
+    sm = a.ship_model
+    full = sm.ship_machinery_model
+    cfg_m = SimplifiedPropulsionMachinerySystemConfiguration(
+        hotel_load=full.hotel_load, machinery_modes=full.machinery_modes, machinery_operating_mode=0,
+        specific_fuel_consumption_coefficients_me=full.fuel_coeffs_for_main_engine,
+        specific_fuel_consumption_coefficients_dg=full.fuel_coeffs_for_diesel_gen,
+        thrust_force_dynamic_time_constant=SIMPLIFIED["thrust_force_dynamic_time_constant"],
+        rudder_angle_to_sway_force_coefficient=full.c_rudder_v, rudder_angle_to_yaw_force_coefficient=full.c_rudder_r,
+        max_rudder_angle_degrees=30)
+    simp = SimplifiedMachineryModel(cfg_m, time_step=dt, initial_thrust_force=SIMPLIFIED["initial_thrust_force"])
+
+    class Adapter:                      # the three calls ShipModelAST makes on its machinery (ship_model.py:882-901)
+        c_rudder_v, c_rudder_r = simp.c_rudder_v, simp.c_rudder_r
+
+        def update_shaft_equation(self, load_perc):
+            simp.update_thrust_force(load_perc)
+
+        def thrust(self):
+            return simp.thrust
+
+        def integrate_differentials(self):
+            simp.integrate_differentials()
+
+    sm.ship_machinery_model = Adapter()
+    ctrl_ = ThrottleFromSpeedSetPointSimplifiedPropulsion(kp=SIMPLIFIED["kp"], ki=SIMPLIFIED["ki"], time_step=dt)
+    cfg = O.ship_config_from_asset(assets[0].__class__(**{**assets[0].__dict__, "ship_model": _with_machinery(sm, full)}))
+    cfg.model_kind = O.MODEL_SIMPLIFIED
+    cfg.kp_ship_speed, cfg.ki_ship_speed, cfg.dt_shaft = SIMPLIFIED["kp"], SIMPLIFIED["ki"], float(dt)
+    states = np.zeros((n_steps, 8))
+    wpt = np.zeros(n_steps, dtype=np.int32)
+    for i in range(n_steps):
+        rud = a.auto_pilot.rudder_angle_from_sampled_route(sm.north, sm.east, sm.yaw_angle)
+        cmd = ctrl_.throttle(speed_set_point=a.desired_forward_speed, measured_speed=sm.forward_speed)
+        sm.update_differentials(engine_throttle=cmd, rudder_angle=rud)
+        sm.integrate_differentials()
+        sm.int.next_time()
+        states[i] = [float(sm.north), float(sm.east), float(sm.yaw_angle), float(sm.forward_speed),
+                     float(sm.sideways_speed), float(sm.yaw_rate), float(simp.thrust), float(a.auto_pilot.navigate.e_ct)]
+        wpt[i] = a.auto_pilot.next_wpt
+    keep = np.unique(np.concatenate([np.arange(min(256, n_steps)), np.arange(15, n_steps, 16), [n_steps - 1]]))
+    meta = dict(kind="simplified", dt=dt, who=0, mode="PTI", **SIMPLIFIED)
+    return dict(cfg=struct_bytes(cfg), n_steps=n_steps, step_index=keep + 1, states=states[keep], next_wpt=wpt,
+                err_i=float(ctrl_.ship_speed_controller.error_i), meta=json.dumps(meta))
+
+
+def _with_machinery(sm, full):
+    """A shallow view of the ship model that still exposes the detailed machinery object, for config extraction."""
+    import copy
+    v = copy.copy(sm)
+    v.ship_machinery_model = full
+    return v
+
+
+def main_simplified():
+    H.install_stubs()
+    out = bare_simplified(4, 4000)
+    np.savez_compressed(os.path.join(HERE, "bare_simplified_dt4_test.npz"), **out)
+    print("simplified", out["states"][-1])
+
+
 def main_logs():
     H.install_stubs()
     for kind in ("colav", "rl"):
@@ -369,7 +446,10 @@ if __name__ == "__main__":
         main_sampler()      # only the sampler fixtures (the others are unchanged)
     elif len(sys.argv) > 1 and sys.argv[1] == "logs":
         main_logs()
+    elif len(sys.argv) > 1 and sys.argv[1] == "simplified":
+        main_simplified()
     else:
         main()
         main_sampler()
         main_logs()
+        main_simplified()

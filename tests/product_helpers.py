@@ -45,8 +45,8 @@ def assets_from_meta(meta):
 def product_ship_vec(env, role, e=0) -> np.ndarray:
     """[N, E, psi, u, v, r, omega, e_ct] of one ship, in the layout of helpers.STATE_SCALE."""
     s = env.ship_f64[:, 2 * e + role].cpu().numpy()
-    detailed = env._params.ship[0].model_kind == L.MODEL_DETAILED
-    return np.array([s[0], s[1], s[2], s[3], s[4], s[5], s[6] if detailed else 0.0, s[8]])
+    has_machinery_state = env._params.ship[0].model_kind != L.MODEL_SIMPLE     # shaft speed or thrust force
+    return np.array([s[0], s[1], s[2], s[3], s[4], s[5], s[6] if has_machinery_state else 0.0, s[8]])
 
 
 def product_ctrl_vec(env, role, e=0) -> np.ndarray:

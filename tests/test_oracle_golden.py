@@ -17,6 +17,16 @@ def test_bare_ship_rollout(name):
     g = golden(name)
     cfg = struct_from_bytes(O.ShipConfig, g["cfg"])
     n = int(g["n_steps"])
+    if cfg.model_kind == O.MODEL_SIMPLIFIED:
+        # A8': hull + SimplifiedMachineryModel (thrust-force state in the omega column), see make_golden.py
+        import json
+        meta = json.loads(str(g["meta"]))
+        out, wpt, st = O.simplified_rollout(cfg, meta["thrust_force_dynamic_time_constant"], meta["initial_thrust_force"], n)
+        err = rel_err(out[g["step_index"] - 1], g["states"], STATE_SCALE)
+        assert err.max() < REL_TOL, (name, err.max(axis=0))
+        assert rel_err(st.spd_err_i, float(g["err_i"]), 1.0) < REL_TOL
+        assert np.array_equal(wpt, g["next_wpt"])
+        return
     out, wpt, st = O.ship_rollout(cfg, n)
     idx = g["step_index"] - 1
     err = rel_err(out[idx], g["states"], STATE_SCALE)
