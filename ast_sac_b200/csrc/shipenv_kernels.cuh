@@ -88,11 +88,20 @@ __device__ __forceinline__ void load_segment_points(const Route& rt, int n_iw, S
   route_wp(rt, n_iw, s.k, s.wn, s.we);
 }
 
+// bearing of a segment and its sin / cos (LOS_guidance.py:105-107).  (Moving this and the polygon edge loops out
+// of line to shrink the simulator loop's instruction footprint was measured: -13 % code, but the call overhead
+// and extra spills cost 1-2 %; see profiles/r01_ncu_summary.md part 2.)
+__device__ __forceinline__ double3 segment_bearing(double dx, double dy) {
+  double3 out;
+  out.x = atan2(dy, dx);
+  senv_sincos(out.x, &out.y, &out.z);
+  return out;                                                // by value: alpha, sin, cos stay in registers
+}
+
 __device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship& s) {
   load_segment_points(rt, n_iw, s);
-  const double dx = s.wn - s.pn, dy = s.we - s.pe;
-  s.alpha = atan2(dy, dx);                                   // LOS_guidance.py:105-107
-  senv_sincos(s.alpha, &s.sin_a, &s.cos_a);
+  const double3 b = segment_bearing(s.wn - s.pn, s.we - s.pe);
+  s.alpha = b.x; s.sin_a = b.y; s.cos_a = b.z;
 }
 
 __device__ __forceinline__ double sat(double val, double low, double hi) {   // controllers.py:67-72
@@ -397,9 +406,21 @@ __device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, 
 // is_pos_inside_obstacles (check_condition.py:48-78): is any of the four corners of the L x L square
 // around the ship inside any polygon.  One pass over a polygon's edges serves all four corners (two
 // distinct y values -> two crossing abscissae per edge, each compared with the two x values).
+__device__ __forceinline__ bool pos_inside_obstacles_slow(const double* ve, const double* vn, const int* start,
+                                                          const double* bbox, unsigned mask, double n, double e,
+                                                          double ship_length);
+
+// the common case (no polygon near the ship's grid cell) stays inline; the edge loops are out of line
 __device__ __forceinline__ bool pos_inside_obstacles(const MapView& mp, unsigned mask, double n, double e,
                                                      double ship_length) {
   if (mask == 0) return false;
+  return pos_inside_obstacles_slow(mp.ve, mp.vn, mp.start, mp.bbox, mask, n, e, ship_length);
+}
+
+__device__ __forceinline__ bool pos_inside_obstacles_slow(const double* ve, const double* vn, const int* start,
+                                                          const double* bbox, unsigned mask, double n, double e,
+                                                          double ship_length) {
+  struct { const double* ve; const double* vn; const int* start; const double* bbox; } mp{ve, vn, start, bbox};
   const double margin = ship_length / 2;
   const double y0 = n - margin, x0 = e - margin, y1 = n + margin, x1 = e + margin;
   while (mask) {
@@ -600,6 +621,7 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
   __syncthreads();
   for (int p = threadIdx.x; p < sb.p.n_poly; p += blockDim.x) {
     double mne = INFINITY, mxe = -INFINITY, mnn = INFINITY, mxn = -INFINITY;
+#pragma unroll 1
     for (int i = sb.p.poly_start[p]; i < sb.p.poly_start[p + 1]; ++i) {
       mne = fmin(mne, sb.p.vert_e[i]); mxe = fmax(mxe, sb.p.vert_e[i]);
       mnn = fmin(mnn, sb.p.vert_n[i]); mxn = fmax(mxn, sb.p.vert_n[i]);
@@ -1133,15 +1155,14 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (IS_RL) {
         const double gd = map_distance(mp, s.north, s.east);
         const double aect = fabs(s.e_ct);
-        if (role == 0) {
-          // test_ship_grounding_reward / test_ship_nav_failure_reward (reward_function.py:359-425)
-          if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : exp(-(gd * gd) / 175000.0);
-          rb = (aect < 3000.0) ? exp(-((aect - 3000.0) * (aect - 3000.0)) / 1250000.0) : 1.0;
-        } else {
-          // obs_ship_grounding_reward / obs_ship_nav_failure_reward (reward_function.py:427-494)
-          if (gd <= 1000.0) ra = -((gd < 0.0) ? 1.0 : exp(-(gd * gd) / 50000.0));
-          rb = -((aect < 500.0) ? exp(-((aect - 500.0) * (aect - 500.0)) / 12500.0) : 1.0);
-        }
+        // test_ship_grounding_reward / test_ship_nav_failure_reward (reward_function.py:359-425) on the test lane,
+        // obs_ship_grounding_reward / obs_ship_nav_failure_reward (:427-494, negated) on the obstacle lane:
+        // RewardDesign3/4 with per-role constants, one exp() call site for both roles
+        const double g_scale = role == 0 ? 175000.0 : 50000.0;
+        const double n_tol = role == 0 ? 3000.0 : 500.0, n_scale = role == 0 ? 1250000.0 : 12500.0;
+        if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : exp(-(gd * gd) / g_scale);
+        rb = (aect < n_tol) ? exp(-((aect - n_tol) * (aect - n_tol)) / n_scale) : 1.0;
+        if (role == 1) { ra = -ra; rb = -rb; }
       }
     }
     const int p_flags = __shfl_xor_sync(FULL_MASK, my_flags, 1);
