@@ -335,6 +335,7 @@ __device__ __forceinline__ bool poly_contains(const MapView& mp, int p, double x
   const int a = mp.start[p], b = mp.start[p + 1];
   bool inside = false;
   double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
+#pragma unroll 1
   for (int i = a; i < b; ++i) {
     const double xi = mp.ve[i], yi = mp.vn[i];
     if ((yi > y) != (yj > y)) {
@@ -432,6 +433,9 @@ __device__ __forceinline__ bool pos_inside_obstacles_slow(const double* ve, cons
     const int a = mp.start[p], b = mp.start[p + 1];
     unsigned in = 0;   // bit 0: (y0,x0)  bit 1: (y0,x1)  bit 2: (y1,x0)  bit 3: (y1,x1)
     double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
+    // not unrolled: the loop runs only for ships next to a polygon, and its unrolled body (8 FP64 divisions) put
+    // 11 KB of rarely executed code into the simulator loop's instruction-cache footprint
+#pragma unroll 1
     for (int i = a; i < b; ++i) {
       const double xi = mp.ve[i], yi = mp.vn[i];
       if ((yi > y0) != (yj > y0)) {
@@ -485,9 +489,12 @@ __device__ __forceinline__ double wrap_pmpi(double a) {     // wrap_angle_to_pmp
   return -kPi + py_mod(a - (-kPi), kPi - (-kPi));
 }
 
+#ifndef SENV_SBMPC_INLINE
+#define SENV_SBMPC_INLINE __forceinline__
+#endif
 // cost of behaviour b (SBMPC.cost_func, sbmpc.py:190-296, for the prediction of linear_pred,
 // sbmpc_misc.py:102-122, against Obstacle.calculate_trajectory, sbmpc_misc.py:58-83)
-__device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, double obs_l, double obs_w) {
+__device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b, double obs_l, double obs_w) {
   const int ic = b >> 2, jp = b & 3;
   const double chi_ca = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);       // np.deg2rad(Chi_ca_[ic])
   const double p_ca = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
@@ -497,17 +504,22 @@ __device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, dou
   const double cos_ot = 0.9997823068017366;                 // np.cos(np.deg2rad(PHI_OT_)): degrees applied twice
   // obstacle: constant velocity along its heading
   double so, co;
-  sincos(in.ob_psi, &so, &co);
+  senv_sincos(in.ob_psi, &so, &co);
   const double ob_dx = ((-so) * in.ob_u + co * in.ob_v) * kSbDt;
   const double ob_dy = (co * in.ob_u + so * in.ob_v) * kSbDt;
   const double vo0 = (-so) * in.ob_u + co * in.ob_v, vo1 = co * in.ob_u + so * in.ob_v;   // rot2d, sbmpc.py:312-314
   const double n_vo = sqrt(vo0 * vo0 + vo1 * vo1);
   // own ship: heading psi_d from sample 1 on, wrapped heading and the measured sway speed at sample 0
   const double ud = in.u_d * p_ca, psi_d = in.chi_d + chi_ca;
-  const double psi0 = wrap_pmpi(psi_d);
   double s0, c0, sd, cd;
-  sincos(psi0, &s0, &c0);
-  sincos(psi_d, &sd, &cd);
+  senv_sincos(psi_d, &sd, &cd);
+#if SENV_FAST_MATH
+  // sample 0 uses the wrapped heading wrap(psi_d) (sbmpc_misc.py:109): same angle modulo 2 pi, so the same sin / cos
+  // up to the rounding of the wrap
+  s0 = sd; c0 = cd;
+#else
+  senv_sincos(wrap_pmpi(psi_d), &s0, &c0);
+#endif
   const double zero = 0.0;
   const double os_dx1 = kSbDt * ((-sd) * ud + cd * in.os_v), os_dy1 = kSbDt * (cd * ud + sd * in.os_v);   // 0 -> 1
   const double os_dx = kSbDt * ((-sd) * ud + cd * zero), os_dy = kSbDt * (cd * ud + sd * zero);           // i -> i+1
@@ -567,6 +579,32 @@ __device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, dou
   sample(ox - sx, oy - sy, kSbDt, otA, ccA);                                   // i = 0: measured state
   sx = sx + os_dx1; sy = sy + os_dy1; ox = ox + ob_dx; oy = oy + ob_dy;
   sample(ox - sx, oy - sy, 2 * kSbDt, otB, ccB);                               // i = 1
+#if SENV_FAST_MATH
+  // From sample 1 on both ships move on straight lines: the offset is e_1 + k w (k = i - 1), so the samples that
+  // can lie within ds_far form one window of k, the roots of |e_1 + k w|^2 = far^2 widened by a sample on either
+  // side.  Samples outside it contribute nothing (see above) and are not visited; positions inside it are taken as
+  // e_1 + k w instead of k sequential additions (differs by the rounding of the additions, ~1e-12 m).
+  {
+    const double e10 = ox - sx, e11 = oy - sy;
+    const double w0 = ob_dx - os_dx, w1 = ob_dy - os_dy;
+    const double qa = w0 * w0 + w1 * w1, qb = e10 * w0 + e11 * w1, qc = e10 * e10 + e11 * e11 - far2 * 1.000001;
+    int k_lo = 1, k_hi = kSbSamples - 2;                       // k = 0 (sample 1) is done
+    if (qa > 0.0) {
+      const double disc = qb * qb - qa * qc;
+      if (disc < 0.0) k_hi = 0;                                // never that close
+      else {
+        const double root = sqrt(disc), inv = 1.0 / qa;
+        const double lo = (-qb - root) * inv - 1.0, hi = (-qb + root) * inv + 1.0;
+        if (lo > (double)k_lo) k_lo = (lo < 1.0e6) ? (int)lo : kSbSamples;
+        if (hi < (double)k_hi) k_hi = (hi > -1.0e6) ? (int)ceil(hi) : 0;
+      }
+    } else if (!(qc < 0.0)) k_hi = 0;                          // no relative motion and out of range
+    for (int k = k_lo; k <= k_hi; ++k) {
+      const double kk = (double)k;
+      sample(e10 + kk * w0, e11 + kk * w1, (kk + 2.0) * kSbDt, otB, ccB);
+    }
+  }
+#else
   double t = 2 * kSbDt;
 #pragma unroll 2
   for (int i = 2; i < kSbSamples; ++i) {
@@ -574,6 +612,7 @@ __device__ __noinline__ double sbmpc_behaviour_cost(const SbmpcIn in, int b, dou
     t += kSbDt;
     sample(ox - sx, oy - sy, t, otB, ccB);
   }
+#endif
   const double d_chi = chi_ca - in.chi_last;                // delta_Chi, sbmpc.py:303-310
   double dl_chi = 0.0;
   if (d_chi > 0) dl_chi = 20.0 * (d_chi * d_chi);
@@ -913,8 +952,11 @@ k_prologue(DevView dv, const double* __restrict__ actions) {
 // ------------------------------------------------------------------------------------------------
 enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 
+#ifndef SENV_MIN_BLOCKS_SBMPC
+#define SENV_MIN_BLOCKS_SBMPC 4   // measured: 3 CTAs/SM (168 registers, fewer spills) speeds the inactive steps up but slows the evaluation
+#endif
 template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
-__global__ void __launch_bounds__(128, SENV_MIN_BLOCKS)
+__global__ void __launch_bounds__(128, SBMPC ? SENV_MIN_BLOCKS_SBMPC : SENV_MIN_BLOCKS)
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
   __shared__ SharedBlock sb;
   stage_params(sb, dv.params);
