@@ -387,7 +387,7 @@ def run_b200(a, rank, local_rank, world):
                        "env_steps_per_episode_mean": env_steps_per_episode / B,
                        "wall_s_timed_region": float(allagg[:, 2].max())},
             "clocks": clocks,
-            "gpu_launches": int(a.steps * (1 + N_RL_STEPS)),
+            "gpu_launches": int(a.steps * (1 + 2 * N_RL_STEPS)),     # k_reset + 9 x (k_prologue + k_env) per episode
             "launch_ms_mean": [round(float(x), 4) for x in launch_ms.mean(axis=0)],
             "launch_env_steps": [int(x) for x in launch_steps.tolist()],
             "roofline": roofline, "roofline_hbm_k1": roofline_k1,
