@@ -13,7 +13,8 @@ import torch
 class BatchRLAlgorithm:
     def __init__(self, trainer, exploration_data_collector, evaluation_data_collector, replay_buffer, batch_size,
                  max_path_length, num_epochs, num_eval_steps_per_epoch, num_expl_steps_per_train_loop,
-                 num_trains_per_train_loop, num_train_loops_per_epoch=1, min_num_steps_before_training=0, log=print):
+                 num_trains_per_train_loop, num_train_loops_per_epoch=1, min_num_steps_before_training=0, log=print,
+                 use_cuda_graph=False):
         self.trainer = trainer
         self.expl_data_collector, self.eval_data_collector = exploration_data_collector, evaluation_data_collector
         self.replay_buffer = replay_buffer
@@ -24,6 +25,7 @@ class BatchRLAlgorithm:
         self.num_train_loops_per_epoch = num_train_loops_per_epoch
         self.min_num_steps_before_training = min_num_steps_before_training
         self.log = log
+        self.use_cuda_graph = use_cuda_graph
         self.history = []
 
     def _sync(self):
@@ -49,8 +51,13 @@ class BatchRLAlgorithm:
                 self.expl_data_collector.collect_new_steps(self.max_path_length, self.num_expl_steps_per_train_loop, False)
                 self._sync()
                 tb = time.perf_counter()
+                if self.use_cuda_graph and self.trainer._graph is None:
+                    self.trainer.capture(self.replay_buffer, self.batch_size)
                 for _ in range(self.num_trains_per_train_loop):
-                    self.trainer.train_from_torch(self.replay_buffer.random_batch(self.batch_size))
+                    if self.use_cuda_graph:
+                        self.trainer.train_graphed()
+                    else:
+                        self.trainer.train_from_torch(self.replay_buffer.random_batch(self.batch_size))
                 self._sync()
                 tc = time.perf_counter()
                 t_expl += tb - ta

@@ -44,8 +44,11 @@ class GpuReplayBuffer:
         # ring position and fill level live on the device so that appends never synchronise
         self._top_dev = torch.zeros((), dtype=torch.int64, device=self.device)
         self._size_dev = torch.zeros((), dtype=torch.int64, device=self.device)
-        self._gen = torch.Generator(device=self.device)
+        # a private generator only when a seed is asked for; the default generator is the one CUDA graph capture
+        # knows how to advance between replays
+        self._gen = None
         if seed is not None:
+            self._gen = torch.Generator(device=self.device)
             self._gen.manual_seed(seed)
 
     # -- reference API (single samples / paths; host values accepted) -------------------------------

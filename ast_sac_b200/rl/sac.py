@@ -115,7 +115,7 @@ class SACTrainer:
     def __init__(self, env, policy, qf1, qf2, target_qf1, target_qf2, discount=0.99, reward_scale=1.0,
                  policy_lr=1e-3, qf_lr=1e-3, soft_target_tau=1e-2, target_update_period=1,
                  use_automatic_entropy_tuning=True, target_entropy=None, action_reg_coeff=None, clip_val=np.inf,
-                 device=None):
+                 device=None, capturable=False):
         self.policy, self.qf1, self.qf2 = policy, qf1, qf2
         self.target_qf1, self.target_qf2 = target_qf1, target_qf2
         # (like the reference, the target networks keep their own random initialisation: ast-sac_runner.py:134-145)
@@ -125,10 +125,11 @@ class SACTrainer:
         if use_automatic_entropy_tuning:
             self.target_entropy = (-float(np.prod(env.action_space.shape)) if target_entropy is None else target_entropy)
             self.log_alpha = torch.zeros(1, requires_grad=True, device=dev)
-            self.alpha_optimizer = torch.optim.Adam([self.log_alpha], lr=policy_lr)
-        self.policy_optimizer = torch.optim.Adam(policy.parameters(), lr=policy_lr)
-        self.qf1_optimizer = torch.optim.Adam(qf1.parameters(), lr=qf_lr)
-        self.qf2_optimizer = torch.optim.Adam(qf2.parameters(), lr=qf_lr)
+            self.alpha_optimizer = torch.optim.Adam([self.log_alpha], lr=policy_lr, capturable=capturable)
+        self.policy_optimizer = torch.optim.Adam(policy.parameters(), lr=policy_lr, capturable=capturable)
+        self.qf1_optimizer = torch.optim.Adam(qf1.parameters(), lr=qf_lr, capturable=capturable)
+        self.qf2_optimizer = torch.optim.Adam(qf2.parameters(), lr=qf_lr, capturable=capturable)
+        self._graph = None
         self.discount, self.reward_scale = discount, reward_scale
         self.action_reg_coeff, self.clip_val = action_reg_coeff, clip_val
         self._n_train_steps_total = 0
@@ -183,6 +184,32 @@ class SACTrainer:
         self._last = tuple(x.detach() if torch.is_tensor(x) else x for x in (policy_loss, qf1_loss, qf2_loss, alpha, log_pi, q1_pred))
 
     train = train_from_torch
+
+    # -- one CUDA graph per update (stock torch.cuda.graphs): sample a batch from the GPU replay buffer + the whole
+    # update above.  The five MLPs are tiny (9 -> 256 -> 256 -> 1, batch 256), so an eager update is ~100 kernel
+    # launches of a few microseconds each; replaying them as one graph removes the launch overhead.
+    def capture(self, replay_buffer, batch_size, warmup=3):
+        if self.target_update_period != 1:
+            raise ValueError("graph capture assumes target_update_period == 1 (the reference default)")
+        if not self.policy_optimizer.defaults.get("capturable", False):
+            raise ValueError("construct the trainer with capturable=True to capture its optimizers")
+        dev = next(self.policy.parameters()).device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_from_torch(replay_buffer.random_batch(batch_size))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.train_from_torch(replay_buffer.random_batch(batch_size))
+        self._graph = graph
+        self._n_train_steps_total -= 1          # the capture pass itself does not run the kernels
+        return graph
+
+    def train_graphed(self):
+        self._graph.replay()
+        self._n_train_steps_total += 1
 
     def get_diagnostics(self):
         if not hasattr(self, "_last"):

@@ -45,6 +45,7 @@ def parse():
     p.add_argument('--action_reg_coeff', type=float, default=0.01)
     p.add_argument('--clip_val', type=float, default=100)
     p.add_argument('--seed', type=int, default=0)
+    p.add_argument('--cuda_graph', type=int, default=1, help="replay each SAC update as one CUDA graph (0: eager)")
     return p.parse_args()
 
 
@@ -60,10 +61,11 @@ def main():
     M = a.layer_size
     qf1, qf2, tq1, tq2 = (ConcatMlp([M, M], 1, 9).to(dev) for _ in range(4))
     policy = TanhGaussianPolicy([M, M], obs_dim=8, action_dim=1).to(dev)
-    buf = GpuReplayBuffer(a.replay_buffer_size, env=wrapped, seed=a.seed)
+    buf = GpuReplayBuffer(a.replay_buffer_size, env=wrapped, seed=None if a.cuda_graph else a.seed)
     trainer = SACTrainer(wrapped, policy, qf1, qf2, tq1, tq2, discount=a.discount, reward_scale=a.reward_scale,
                          policy_lr=a.policy_lr, qf_lr=a.qf_lr, soft_target_tau=a.soft_target_tau,
-                         target_update_period=a.target_update_period, action_reg_coeff=a.action_reg_coeff, clip_val=a.clip_val)
+                         target_update_period=a.target_update_period, action_reg_coeff=a.action_reg_coeff, clip_val=a.clip_val,
+                         capturable=bool(a.cuda_graph))
     expl = VectorizedPathCollector(wrapped, policy, replay_buffer=buf)
     evalc = VectorizedPathCollector(wrapped, MakeDeterministic(policy))
     c0 = env.total_substeps()
@@ -73,7 +75,7 @@ def main():
                            num_expl_steps_per_train_loop=a.num_expl_steps_per_train_loop,
                            num_trains_per_train_loop=a.num_trains_per_train_loop,
                            min_num_steps_before_training=a.min_num_steps_before_training,
-                           log=lambda s: print(json.dumps(s), flush=True))
+                           log=lambda s: print(json.dumps(s), flush=True), use_cuda_graph=bool(a.cuda_graph))
     hist = alg.train()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
@@ -85,7 +87,8 @@ def main():
                       "rl_transitions": expl._num_steps_total + evalc._num_steps_total, "simulator_steps": sim_steps,
                       "rollout_s": t_roll, "training_s": t_train,
                       "env_steps_per_s_in_rollouts": sim_steps / max(t_roll, 1e-9),
-                      "sac_updates_per_s": trainer._n_train_steps_total / max(t_train, 1e-9)}), flush=True)
+                      "sac_updates_per_s": trainer._n_train_steps_total / max(t_train, 1e-9),
+                      "cuda_graph": bool(a.cuda_graph)}), flush=True)
     env.close()
 
 
