@@ -625,3 +625,87 @@ def test_trajectory_log_matches_reference_simulation_results(kind):
     _sync()
     assert int(env.log_count[0]) == 1 and int(env.log_count[1]) == 1       # reset() starts a new log; init_step logs one row
     env.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# NonIW env (config 1) batched: _step() in chunks against per-environment oracle runs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("collav", ["none", "simple", "sbmpc"])
+def test_noniw_batched_substeps_match_oracle(collav):
+    """64 MultiShipNonIWEnv copies with jittered starts, init_step() + _step(k) launches of uneven k until every
+    environment is done; step counts, events and flags bit-exact against the oracle, states within REL_TOL.
+    Under SBMPC both ships call the collision avoidance in turn (the obstacle ship's call sees the state the test
+    ship has just integrated to): the two-phase path of the kernel."""
+    B = 64
+    args = S.get_env_args(time_step=4, collav_mode=collav)
+    assets, m = S.build_colav_assets(args, iw=False)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=80.0, seed=5)
+    env, assets = S.prepare_colav_env(args, iw=False, num_envs=B, init_states=init)
+    base_cfg = _oracle_cfg(assets, env, O.ENV_COLAV_NONIW)
+    init_np = init.cpu().numpy().reshape(7, B, 2)
+    oracles, n_or, res = [], np.zeros(B, dtype=np.int64), [None] * B
+    for b in range(B):
+        cfg = O.EnvConfig()
+        C.memmove(C.byref(cfg), C.byref(base_cfg), C.sizeof(O.EnvConfig))
+        for role in range(2):
+            cfg.ship[role].initial_north_position_m = init_np[0, b, role]
+            cfg.ship[role].initial_east_position_m = init_np[1, b, role]
+        oe = O.OracleEnv(cfg)
+        oe.init_step()
+        oracles.append(oe)
+    env.init_step()
+    total, chunk = 0, [1, 7, 64, 300, 129]
+    it = 0
+    while not bool(env.done_mask.all()) and total < 6000:
+        k = chunk[it % len(chunk)]
+        it += 1
+        env._step(k)
+        _sync()
+        total += k
+        nsub = env.nsub_buf.cpu().numpy()
+        info = env.info_buf.cpu().numpy()
+        states = product_states_all(env)
+        kk = env.next_wpt.cpu().numpy()
+        for b in range(B):
+            for _ in range(int(nsub[b])):
+                res[b] = oracles[b]._step()
+                n_or[b] += 1
+            if nsub[b] == 0:
+                continue
+            r, st = res[b], oracles[b].st
+            assert (info[b] & L.INFO_EVENT_MASK) == r.events and bool(info[b] & L.INFO_DONE) == bool(r.done), (collav, b, total)
+            assert bool(info[b] & L.INFO_TERMINAL) == bool(r.terminal)
+            assert kk[b, 0] == st.ship[0].next_wpt and kk[b, 1] == st.ship[1].next_wpt
+            for role in range(2):
+                e = rel_err(states[b, role], oracle_ship_vec(st.ship[role]), STATE_SCALE)
+                assert e.max() < REL_TOL, (collav, b, total, role, e)
+            # an environment that is done stops early inside the launch: the oracle stopped at the same step
+            assert bool(r.done) or nsub[b] == k
+    assert bool(env.done_mask.all())
+    assert env.total_substeps() == int(n_or.sum())
+    env.close()
+
+
+def test_substeps_split_invariance_with_sbmpc():
+    """SBMPC keeps state between simulator steps (P_ca_last_, Chi_ca_last_): k x _step() in one launch must equal the
+    same steps over several launches bit for bit, with the memory round-tripping through HBM."""
+    B = 2048
+    args = S.get_env_args(time_step=4, collav_mode="sbmpc")
+    assets, _ = S.build_colav_assets(args, iw=True)
+    # start the obstacle ship 100-250 m ahead of the test ship, head-on: SBMPC manoeuvres from the first step
+    init = S.jittered_init_states(assets, B, pos_jitter_m=60.0, seed=9)
+    init_v = init.view(7, B, 2)
+    gap = torch.linspace(70.0, 180.0, B, dtype=torch.float64, device=init.device)
+    init_v[0, :, 1] = init_v[0, :, 0] + gap
+    init_v[1, :, 1] = init_v[1, :, 0] + gap
+    env_a, _ = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init)
+    env_b, _ = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init)
+    env_a.init_step(); env_b.init_step()
+    env_a._step(60)
+    for k in (1, 9, 20, 30):
+        env_b._step(k)
+    _sync()
+    assert torch.equal(env_a.ship_f64, env_b.ship_f64) and torch.equal(env_a.env_f64, env_b.env_f64)
+    sb = env_a.env_f64[[L.EF["sb_p_last"], L.EF["sb_chi_last"]]]
+    assert bool(((sb[0] != 1.0) | (sb[1] != 0.0)).any()), "SBMPC never chose a manoeuvre: the scenario does not exercise it"
+    env_a.close(); env_b.close()
