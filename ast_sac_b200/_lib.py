@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 6
+ABI_VERSION = 7
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED, MODEL_SIMPLIFIED = 0, 1, 2
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
@@ -27,8 +27,9 @@ SF = dict(north=0, east=1, yaw=2, u=3, v=4, r=5, omega=6, time=7, e_ct=8, e_ct_i
 SF_COUNT = 17
 LOG_COLS = ("time", "north", "east", "yaw", "rudder", "u", "v", "r", "omega", "cmd", "e_ct", "e_psi")
 EF = dict(travel_dist=0, travel_time=1, acc_reward=2, n_base=3, e_base=4, log_north=5, log_east=6, sb_p_last=7,
-          sb_chi_last=8)
-EF_COUNT = 9
+          sb_chi_last=8, seg_new_alpha=9, seg_new_sin=10, seg_new_cos=11, seg_end_alpha=12, seg_end_sin=13,
+          seg_end_cos=14)
+EF_COUNT = 15
 EI = dict(sampling_count=0, snapshot_info=1, flags=2)
 EI_COUNT = 3
 

@@ -72,6 +72,10 @@ struct Route {            // route of this lane: fixed file waypoints + per-env 
   const double* iw_e;
   long long stride;
   int n_file;
+  // bearings: of the file route's segments (shared memory, [k][3] = alpha, sin, cos of wp[k-1] -> wp[k]) and of
+  // the two segments at the newest sampled waypoint (env_f64 rows SEG_NEW_* / SEG_END_* of this environment)
+  const double* seg_file;
+  const double* seg_env;
 };
 
 __device__ __forceinline__ void route_wp(const Route& rt, int n_iw, int idx, double& n, double& e) {
@@ -98,10 +102,23 @@ __device__ __forceinline__ double3 segment_bearing(double dx, double dy) {
   return out;                                                // by value: alpha, sin, cos stay in registers
 }
 
+// New target waypoint: end points and bearing of the segment.  The bearings of the file route's segments are
+// tabulated once per CTA, those of the segments at the newest sampled waypoint by the step() prologue -- the values
+// LOS_guidance.py:105-110 computes, without an atan2 + sincos for a single lane of the warp at every waypoint switch.
 __device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship& s) {
   load_segment_points(rt, n_iw, s);
-  const double3 b = segment_bearing(s.wn - s.pn, s.we - s.pe);
-  s.alpha = b.x; s.sin_a = b.y; s.cos_a = b.z;
+  const int head = rt.n_file - 1;
+  if (n_iw == 0 || s.k < head) {
+    s.alpha = rt.seg_file[3 * s.k]; s.sin_a = rt.seg_file[3 * s.k + 1]; s.cos_a = rt.seg_file[3 * s.k + 2];
+  } else if (s.k >= head + n_iw - 1 && rt.seg_env) {
+    const int row = (s.k == head + n_iw) ? SHIPENV_EF_SEG_END_ALPHA : SHIPENV_EF_SEG_NEW_ALPHA;
+    s.alpha = rt.seg_env[(long long)row * rt.stride];
+    s.sin_a = rt.seg_env[(long long)(row + 1) * rt.stride];
+    s.cos_a = rt.seg_env[(long long)(row + 2) * rt.stride];
+  } else {                                                   // an older sampled segment: not tabulated
+    const double3 b = segment_bearing(s.wn - s.pn, s.we - s.pe);
+    s.alpha = b.x; s.sin_a = b.y; s.cos_a = b.z;
+  }
 }
 
 __device__ __forceinline__ double sat(double val, double low, double hi) {   // controllers.py:67-72
@@ -649,6 +666,7 @@ __device__ __forceinline__ int sbmpc_warp_argmin(const SbmpcIn& mine, int src, i
 struct SharedBlock {
   ShipEnvParams p;
   double bbox[SHIPENV_MAX_POLY * 4];
+  double seg[2][SHIPENV_MAX_WP][3];      // per ship: bearing, sin, cos of the file route's segment wp[k-1] -> wp[k]
   unsigned char next[SHIPENV_MAX_VERT];
 };
 
@@ -668,6 +686,14 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     sb.bbox[4 * p + 0] = mne; sb.bbox[4 * p + 1] = mxe; sb.bbox[4 * p + 2] = mnn; sb.bbox[4 * p + 3] = mxn;
     for (int i = sb.p.poly_start[p]; i < sb.p.poly_start[p + 1]; ++i)
       sb.next[i] = (unsigned char)((i + 1 < sb.p.poly_start[p + 1]) ? i + 1 : sb.p.poly_start[p]);
+  }
+  for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
+    const int r = i / SHIPENV_MAX_WP, k = i % SHIPENV_MAX_WP;
+    const ShipEnvShipParams& P = sb.p.ship[r];
+    if (k >= 1 && k < P.n_wp) {
+      const double3 b = segment_bearing(P.wp_north[k] - P.wp_north[k - 1], P.wp_east[k] - P.wp_east[k - 1]);
+      sb.seg[r][k][0] = b.x; sb.seg[r][k][1] = b.y; sb.seg[r][k][2] = b.z;
+    }
   }
   __syncthreads();
 }
@@ -785,7 +811,8 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
   const ShipEnvShipParams& P = sb.p.ship[role];
   const bool dynamic_route = (role == 1) && (sb.p.env_kind != SHIPENV_ENV_COLAV_NONIW);
   Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
-           dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * dv.num_envs + env : nullptr, dv.num_envs, P.n_wp};
+           dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * dv.num_envs + env : nullptr, dv.num_envs, P.n_wp,
+           &sb.seg[role][0][0], dynamic_route ? dv.buf.env_f64 + env : nullptr};
   Ship s;
   int log_n = -1;
   if (reinit) {
@@ -914,26 +941,32 @@ k_prologue(DevView dv, const double* __restrict__ actions) {
       if (dv.buf.counters) atomicAdd(&dv.buf.counters[1], 1ull);
     } else {
       if (IS_RL) ef[SHIPENV_EF_ACC_REWARD * B + env] = 0.0;      // rl_env env.py:696
-      // The new waypoint took the route's second-to-last slot.  If the obstacle ship is already heading for
-      // the route's last waypoint (index head + n_iw_old), that index now holds the new waypoint.
+      // The new waypoint took the route's second-to-last slot: bearings of the two segments it creates (previous
+      // waypoint -> new waypoint -> route end), for the autopilot's next waypoint switches.
       const ShipEnvShipParams& P = G.ship[1];
       const long long n_ships = 2 * B, sidx = 2 * env + 1;
-      const int k = dv.buf.ship_i32[sidx] & 0xff;
       const int head = P.n_wp - 1;
-      if (k == head + sampling_count - 1) {
-        double pn, pe;
-        if (k - 1 < head) { pn = P.wp_north[k - 1]; pe = P.wp_east[k - 1]; }
-        else {
-          pn = dv.buf.iw_f64[(long long)(k - 1 - head) * B + env];
-          pe = dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + k - 1 - head) * B + env];
-        }
-        const double alpha = atan2(re - pe, rn - pn);               // LOS_guidance.py:105-107
-        double sa, ca;
-        senv_sincos(alpha, &sa, &ca);
+      const int j = sampling_count - 1;                              // index of the new waypoint among the sampled ones
+      double pn, pe;
+      if (j == 0) { pn = P.wp_north[head - 1]; pe = P.wp_east[head - 1]; }
+      else {
+        pn = dv.buf.iw_f64[(long long)(j - 1) * B + env];
+        pe = dv.buf.iw_f64[((long long)SHIPENV_MAX_IW + j - 1) * B + env];
+      }
+      const double3 bn = segment_bearing(rn - pn, re - pe);         // LOS_guidance.py:105-107
+      const double3 be = segment_bearing(P.wp_north[head] - rn, P.wp_east[head] - re);
+      ef[SHIPENV_EF_SEG_NEW_ALPHA * B + env] = bn.x; ef[SHIPENV_EF_SEG_NEW_SIN * B + env] = bn.y;
+      ef[SHIPENV_EF_SEG_NEW_COS * B + env] = bn.z;
+      ef[SHIPENV_EF_SEG_END_ALPHA * B + env] = be.x; ef[SHIPENV_EF_SEG_END_SIN * B + env] = be.y;
+      ef[SHIPENV_EF_SEG_END_COS * B + env] = be.z;
+      // If the obstacle ship is already heading for the route's last waypoint (index head + j), that index now holds
+      // the new waypoint: its current segment becomes previous -> new.
+      const int k = dv.buf.ship_i32[sidx] & 0xff;
+      if (k == head + j) {
         double* f = dv.buf.ship_f64;
-        f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx] = alpha;
-        f[SHIPENV_SF_SEG_SIN * n_ships + sidx] = sa;
-        f[SHIPENV_SF_SEG_COS * n_ships + sidx] = ca;
+        f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx] = bn.x;
+        f[SHIPENV_SF_SEG_SIN * n_ships + sidx] = bn.y;
+        f[SHIPENV_SF_SEG_COS * n_ships + sidx] = bn.z;
       }
     }
   }
@@ -982,7 +1015,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   // registers of the environment currently held by this lane
   Ship s = Ship{};
   s.k = 1;
-  Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp};
+  Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp, &sb.seg[role][0][0], nullptr};
   double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0;
   double log_n = 0.0, log_e = 0.0;
   int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
@@ -1047,6 +1080,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
       rt.iw_n = dynamic_route ? dv.buf.iw_f64 + env : nullptr;
       rt.iw_e = dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * B + env : nullptr;
+      rt.seg_env = dynamic_route ? dv.buf.env_f64 + env : nullptr;
       n_iw = dynamic_route ? sampling_count : 0;
       s.n_wp = P.n_wp + n_iw;
       u_pre = 0.0; last_stop_branch = false; out_reward = 0.0; out_info = 0; nsub = 0;
@@ -1411,7 +1445,7 @@ k_ship_rollout(DevView dv, int k_steps) {
   if (sidx >= n_ships) return;
   const int role = (int)(sidx & 1);
   const ShipEnvShipParams& P = sb.p.ship[role];
-  const Route rt{P.wp_north, P.wp_east, nullptr, nullptr, dv.num_envs, P.n_wp};
+  const Route rt{P.wp_north, P.wp_east, nullptr, nullptr, dv.num_envs, P.n_wp, &sb.seg[role][0][0], nullptr};
   Ship s;
   load_ship(dv, n_ships, sidx, s);
   s.n_wp = P.n_wp;

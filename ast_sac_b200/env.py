@@ -538,8 +538,12 @@ class BatchedShipEnv:
         if self.ENV_KIND == L.ENV_COLAV_NONIW:
             raise RuntimeError("MultiShipNonIWEnv is stepped with _step(); it takes no actions")
         if getattr(self.args, "normalize_action", False) and action is not None:
-            action = self.do_denormalize_action(action if not isinstance(action, torch.Tensor)
-                                                else action.detach().cpu().numpy())
+            if isinstance(action, torch.Tensor):      # stay on the device: same affine map as env.py:192-196
+                lo = torch.as_tensor(self.action_space.low, device=action.device, dtype=action.dtype)
+                hi = torch.as_tensor(self.action_space.high, device=action.device, dtype=action.dtype)
+                action = (action + 1.0) / 2.0 * (hi - lo) + lo
+            else:
+                action = self.do_denormalize_action(action)
         a = self._actions_tensor(action)
         L.check(L.load().shipenv_step(self._handle, a.data_ptr(), self._stream_ptr()))
         return self._pack_step_result(with_reward=self.ENV_KIND == L.ENV_RL, check_unbound=True)

@@ -36,7 +36,8 @@ def get_data_path(filename: str) -> str:
 
 def get_env_args(max_sampling_frequency=9, time_step=4, radius_of_acceptance=300, lookahead_distance=1000,
                  collav_mode='none', ship_draw=False, time_since_last_ship_drawing=30, normalize_action=False):
-    """run/env_args.py:8-22 (the reference default collav_mode is 'sbmpc', not built yet: SURVEY.md 8f #1)."""
+    """run/env_args.py:8-22.  The reference's default collav_mode is 'sbmpc' (run/ast-sac_runner.py:35); the parity and
+    bench scenarios here default to 'none' and name the mode explicitly."""
     return SimpleNamespace(max_sampling_frequency=max_sampling_frequency, time_step=time_step,
                            radius_of_acceptance=radius_of_acceptance, lookahead_distance=lookahead_distance,
                            collav_mode=collav_mode, ship_draw=ship_draw,
