@@ -991,15 +991,24 @@ enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
 __global__ void __launch_bounds__(128, SBMPC ? SENV_MIN_BLOCKS_SBMPC : SENV_MIN_BLOCKS)
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
-  __shared__ SharedBlock sb;
-  stage_params(sb, dv.params);
+  __shared__ SharedBlock sb_static;
+  stage_params(sb_static, dv.params);
+  const int lane = (int)(threadIdx.x & 31);
+  const int role = (int)(threadIdx.x & 1);
+  // The shared-memory addresses of the parameter block and of this lane's ship parameters are held in two
+  // registers the compiler cannot rematerialise: left alone it recomputed them five times per simulator step
+  // (S2R SR_CgaCtaId + S2R SR_TID.X + LEA + LOP3 + IMAD each time: 30 of the loop's 545 instructions, with the
+  // S2R latency in front of the parameter loads that follow).  Measured +5.7 % (colav_iw) / +8.5 % (rl).  Doing the
+  // same to `role` costs more in spills than the S2R + LOP3 it saves (measured: no gain).
+  unsigned sb_addr = (unsigned)__cvta_generic_to_shared(&sb_static);
+  unsigned p_addr = (unsigned)__cvta_generic_to_shared(&sb_static.p.ship[role]);
+  asm volatile("" : "+r"(sb_addr), "+r"(p_addr));
+  SharedBlock& sb = *reinterpret_cast<SharedBlock*>(__cvta_shared_to_generic(sb_addr));
   const ShipEnvParams& G = sb.p;
+  const ShipEnvShipParams& P = *reinterpret_cast<const ShipEnvShipParams*>(__cvta_shared_to_generic(p_addr));
   const long long B = dv.num_envs;
   const long long n_ships = 2 * B;
   const long long n_slots = ((long long)gridDim.x * blockDim.x) >> 1;
-  const int lane = (int)(threadIdx.x & 31);
-  const int role = (int)(threadIdx.x & 1);
-  const ShipEnvShipParams& P = G.ship[role];
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
   const bool dynamic_route = IS_IW && role == 1;
