@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 7
+ABI_VERSION = 8
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED, MODEL_SIMPLIFIED = 0, 1, 2
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
@@ -135,8 +135,9 @@ def measure_fp64_peak(device: int = 0, repeats: int = 5) -> float:
 
 
 def selftest_math(device: int = 0, n: int = 1 << 24, seed: int = 1):
-    """(sincos, atan) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA math library: fast build, strict build."""
-    out = (C.c_ulonglong * 4)()
+    """(sincos, atan, sqrt, division) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA math library:
+    fast build, then strict build (8 numbers, all expected 0)."""
+    out = (C.c_ulonglong * 8)()
     check(load().shipenv_selftest_math(device, n, seed, out))
     return list(out)
 

@@ -669,11 +669,11 @@ int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long lo
     return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
   CUDA_TRY(cudaSetDevice(device));
   unsigned long long* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, 4 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(dev, 0, 4 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&dev, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(dev, 0, 8 * sizeof(unsigned long long)));
   CUDA_TRY(senv_fast::launch_math_selftest(n, seed, dev, nullptr));
-  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 2, nullptr));
-  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 4, nullptr));
+  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   cudaFree(dev);
   return SHIPENV_OK;
 }

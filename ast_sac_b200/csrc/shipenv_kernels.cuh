@@ -1221,8 +1221,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       const unsigned cell = map_cell_masks(mp, s.north, s.east);
       const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
       const double margin = len / 2;
-      const bool outside = (s.north < G.map_min_n + margin || s.north > G.map_max_n - margin) ||
-                           (s.east < G.map_min_e + margin || s.east > G.map_max_e - margin);
+      // (four comparisons combined without short-circuit branches)
+      const bool outside = ((int)(s.north < G.map_min_n + margin) | (int)(s.north > G.map_max_n - margin) |
+                            (int)(s.east < G.map_min_e + margin) | (int)(s.east > G.map_max_e - margin)) != 0;
       const double dn = s.north - route_end_n, de = s.east - route_end_e;
       // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
       // sqrt(nextafter(40000)) rounds above 200)
@@ -1287,6 +1288,18 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
       bool st_done = false, st_terminal = false;
       out_info = 0;
+      // One test for the common simulator step of a step(action) call: main loop (stage 0), no event bit of either
+      // ship, radius of acceptance not reached, no collision and (run_colav, whose `done` needs both stop flags) no
+      // stop flag set.  Nothing below changes anything then except the reward accumulators.
+#ifdef SENV_NO_PLAIN_STEP
+      const bool plain_step = false;
+#else
+      const bool plain_step = (MODE == MODE_STEP) && (stage == 0) && (((t_flags | o_flags) & 63) == 0) &&
+                              !is_collision && (IS_RL || ((s.stop | p_stop) == 0));
+#endif
+      if (plain_step) {
+        if (IS_RL) { acc_reward += r_total; out_reward = r_total; }
+      } else {
       if (((t_flags | o_flags) & 31) != 0 || is_collision) {
         // ---- something holds: termination reward, events and env_info (reward_function.py:204-314)
         const bool t_ground = t_flags & 1, t_nav = t_flags & 2, o_ground = o_flags & 1, o_nav = o_flags & 2;
@@ -1367,6 +1380,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
         }
       }
+      }   // !plain_step
     }
     } while (!__any_sync(FULL_MASK, finalize || lstate == LS_FETCH));
 
