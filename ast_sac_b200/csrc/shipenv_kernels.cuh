@@ -126,6 +126,22 @@ __device__ __forceinline__ double sat(double val, double low, double hi) {   // 
   return (m > low) ? m : low;
 }
 
+// Per-ship constants the simulator step would otherwise recompute at every step (products and sums of
+// parameters only, evaluated once per CTA by stage_params with the same IEEE operations, so the values are the
+// ones the step computed inline).  derived_of(P) finds the block of the ship whose parameters P refers to: the
+// two blocks are laid out in shared memory with the stride of ShipEnvShipParams, at a fixed distance from it.
+struct Derived {
+  double los_r2, los_r99, los_ra2;        // R * R, 0.99 * R (LOS_guidance.py:111-113), ra * ra (:88-92)
+  double wind_cu, wind_cv, wind_cn;       // -0.3 A_f, -0.42 A_l, -0.096 A_l L (fast build's wind force)
+  double hz_min_n, hz_max_n, hz_min_e, hz_max_e;   // map horizon moved in by half a ship length (check_condition.py:96-119)
+};
+struct DerivedSlot {
+  Derived d;
+  char pad[sizeof(ShipEnvShipParams) - sizeof(Derived)];
+};
+struct SharedBlock;
+__device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P);
+
 // ------------------------------------------------------------------------------------------------
 // one simulator step of one ship: autopilot (LOS + heading PID), speed controller, hull + machinery
 // derivatives, forward Euler.  SURVEY.md Appendix A; ship_model.py:351-416, rl_env ship_model.py:
@@ -135,11 +151,12 @@ __device__ __forceinline__ double sat(double val, double low, double hi) {   // 
 // NavigationSystem.los_guidance on the cached segment wp[k-1] -> wp[k] (LOS_guidance.py:100-117): updates
 // e_ct and the LOS integrator, returns the heading reference.
 __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship& s) {
+  const Derived& D = derived_of(P);
   double e_ct = -(s.north - s.pn) * s.sin_a + (s.east - s.pe) * s.cos_a;
-  const double R = P.los_r;
-  if (e_ct * e_ct >= R * R) e_ct = 0.99 * R;
+  const double R2 = D.los_r2;
+  if (e_ct * e_ct >= R2) e_ct = D.los_r99;
   s.e_ct = e_ct;
-  double delta = SENV_SQRT(R * R - e_ct * e_ct);
+  double delta = SENV_SQRT(R2 - e_ct * e_ct);
   if (!(delta > 1e-6)) delta = 1e-6;
   const double q = SENV_DIV(e_ct, delta);
   if (fabs(s.e_ct_int + q) <= P.los_limit) s.e_ct_int += q;
@@ -156,7 +173,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   // --- NavigationSystem.next_wpt
   {
     const double dn = s.wn - s.north, de = s.we - s.east;
-    if (dn * dn + de * de <= P.los_ra * P.los_ra) {
+    if (dn * dn + de * de <= derived_of(P).los_ra2) {
       if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
     }
   }
@@ -271,9 +288,10 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double u_rw = P.wind_speed * cw - u;
   const double v_rw = P.wind_speed * sw - v;
   const double vmag = SENV_SQRT(u_rw * u_rw + v_rw * v_rw);
-  const double tau_u = (-0.3 * P.proj_area_f) * vmag * u_rw;
-  const double tau_v = (-0.42 * P.proj_area_l) * vmag * v_rw;
-  const double tau_n = (-0.096 * P.proj_area_l * P.l_ship) * u_rw * v_rw;
+  const Derived& D = derived_of(P);
+  const double tau_u = D.wind_cu * vmag * u_rw;
+  const double tau_v = D.wind_cv * vmag * v_rw;
+  const double tau_n = D.wind_cn * u_rw * v_rw;
 #else
   double sw, cw;
   sincos(P.wind_dir - s.yaw, &sw, &cw);
@@ -665,10 +683,18 @@ __device__ __forceinline__ int sbmpc_warp_argmin(const SbmpcIn& mine, int src, i
 // shared-memory staging of the parameter block
 struct SharedBlock {
   ShipEnvParams p;
+  DerivedSlot drv[2];                    // see derived_of()
+  double roa2, seg_len2;                 // roa * roa (check_condition.py:181-204), 2 * AB segment length
   double bbox[SHIPENV_MAX_POLY * 4];
   double seg[2][SHIPENV_MAX_WP][3];      // per ship: bearing, sin, cos of the file route's segment wp[k-1] -> wp[k]
   unsigned char next[SHIPENV_MAX_VERT];
 };
+
+__device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P) {
+  constexpr long long kOffset = (long long)offsetof(SharedBlock, drv) - (long long)offsetof(SharedBlock, p.ship);
+  static_assert(sizeof(DerivedSlot) == sizeof(ShipEnvShipParams), "derived blocks must have the parameter stride");
+  return *reinterpret_cast<const Derived*>(reinterpret_cast<const char*>(&P) + kOffset);
+}
 
 __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
@@ -686,6 +712,16 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     sb.bbox[4 * p + 0] = mne; sb.bbox[4 * p + 1] = mxe; sb.bbox[4 * p + 2] = mnn; sb.bbox[4 * p + 3] = mxn;
     for (int i = sb.p.poly_start[p]; i < sb.p.poly_start[p + 1]; ++i)
       sb.next[i] = (unsigned char)((i + 1 < sb.p.poly_start[p + 1]) ? i + 1 : sb.p.poly_start[p]);
+  }
+  if (threadIdx.x < 2) {
+    const ShipEnvShipParams& P = sb.p.ship[threadIdx.x];
+    Derived& D = sb.drv[threadIdx.x].d;
+    D.los_r2 = P.los_r * P.los_r; D.los_r99 = 0.99 * P.los_r; D.los_ra2 = P.los_ra * P.los_ra;
+    D.wind_cu = -0.3 * P.proj_area_f; D.wind_cv = -0.42 * P.proj_area_l; D.wind_cn = -0.096 * P.proj_area_l * P.l_ship;
+    const double margin = P.l_ship / 2;
+    D.hz_min_n = sb.p.map_min_n + margin; D.hz_max_n = sb.p.map_max_n - margin;
+    D.hz_min_e = sb.p.map_min_e + margin; D.hz_max_e = sb.p.map_max_e - margin;
+    if (threadIdx.x == 0) { sb.roa2 = sb.p.roa * sb.p.roa; sb.seg_len2 = sb.p.ab_segment_length * 2; }
   }
   for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
     const int r = i / SHIPENV_MAX_WP, k = i % SHIPENV_MAX_WP;
@@ -1026,12 +1062,22 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   s.k = 1;
   Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp, &sb.seg[role][0][0], nullptr};
   double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0;
-  double log_n = 0.0, log_e = 0.0;
+  // The travel tracker adds |row_t - row_{t-1}| of the obstacle ship's logged (pre-integration) positions
+  // (env.py:526-534).  That distance is known one step early -- right after the integration of step t-1, as
+  // |position after - position before| (the same subtraction) -- so it is carried as one value (`pending_dist`)
+  // instead of the previous position, which would have to be rotated through registers at every step.  The
+  // previous position itself (LOG_NORTH / LOG_EAST rows of env_f64) and the surge speed before the integration
+  // (obs[6]) are only needed when the environment is stored: they are written to a per-lane shared-memory slot.
+  struct LaneScratch { double log_n, log_e, u_pre, pad; };
+  __shared__ LaneScratch lane_scratch[128];
+  unsigned scratch_addr = (unsigned)__cvta_generic_to_shared(&lane_scratch[threadIdx.x]);
+  asm volatile("" : "+r"(scratch_addr));
+  LaneScratch& scratch = *reinterpret_cast<LaneScratch*>(__cvta_shared_to_generic(scratch_addr));
+  double pending_dist = 0.0;
   int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
   double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)
   int sampling_count = 0, flags = 0, n_iw = 0;
   float ps_tn = 0.f, ps_te = 0.f, ps_on = 0.f, ps_oe = 0.f;
-  double u_pre = 0.0;         // surge speed before the last integration (obs[6])
   bool last_stop_branch = false;
   double out_reward = 0.0;
   int out_info = 0, nsub = 0;
@@ -1074,8 +1120,12 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
       travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
       acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
-      log_n = ef[SHIPENV_EF_LOG_NORTH * B + env];
-      log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+      {
+        const double log_n = ef[SHIPENV_EF_LOG_NORTH * B + env], log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+        scratch.log_n = log_n; scratch.log_e = log_e; scratch.u_pre = 0.0;
+        const double tn = s.north - log_n, te = s.east - log_e;
+        pending_dist = SENV_SQRT(tn * tn + te * te);
+      }
       if (SBMPC) {
         sb_p_last = ef[SHIPENV_EF_SB_P_LAST * B + env];
         sb_chi_last = ef[SHIPENV_EF_SB_CHI_LAST * B + env];
@@ -1092,7 +1142,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       rt.seg_env = dynamic_route ? dv.buf.env_f64 + env : nullptr;
       n_iw = dynamic_route ? sampling_count : 0;
       s.n_wp = P.n_wp + n_iw;
-      u_pre = 0.0; last_stop_branch = false; out_reward = 0.0; out_info = 0; nsub = 0;
+      last_stop_branch = false; out_reward = 0.0; out_info = 0; nsub = 0;
       have_obs = false; stage = 0; have_iw = false; k_left = k_substeps;
       lstate = LS_RUN;
       if (flags & SHIPENV_FLAG_DONE) {
@@ -1184,7 +1234,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         s.time = s.time + dt;
         last_stop_branch = true;
       } else {
-        u_pre = s.u;
+        scratch.u_pre = s.u;
         last_stop_branch = false;
         bool hit = false;
         if (collav_lane) {
@@ -1198,12 +1248,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         if (role == 1 && IS_IW) {
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
-            const double tn = pre_n - log_n, te = pre_e - log_e;
-            travel_dist += SENV_SQRT(tn * tn + te * te);
+            travel_dist += pending_dist;
             travel_time += dt;
           }
+          const double tn = s.north - pre_n, te = s.east - pre_e;
+          pending_dist = SENV_SQRT(tn * tn + te * te);
         }
-        log_n = pre_n; log_e = pre_e;
+        scratch.log_n = pre_n; scratch.log_e = pre_e;
       }
     }
     }
@@ -1220,23 +1271,23 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       const double len = P.l_ship;
       const unsigned cell = map_cell_masks(mp, s.north, s.east);
       const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
-      const double margin = len / 2;
       // (four comparisons combined without short-circuit branches)
-      const bool outside = ((int)(s.north < G.map_min_n + margin) | (int)(s.north > G.map_max_n - margin) |
-                            (int)(s.east < G.map_min_e + margin) | (int)(s.east > G.map_max_e - margin)) != 0;
+      const Derived& D = derived_of(P);
+      const bool outside = ((int)(s.north < D.hz_min_n) | (int)(s.north > D.hz_max_n) |
+                            (int)(s.east < D.hz_min_e) | (int)(s.east > D.hz_max_e)) != 0;
       const double dn = s.north - route_end_n, de = s.east - route_end_e;
       // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
       // sqrt(nextafter(40000)) rounds above 200)
       const bool reached = (dn * dn + de * de) <= 40000.0;
       bool nav_fail = fabs(s.e_ct) > P.nav_fail_tol;
-      if (role == 1) nav_fail = (travel_dist > G.ab_segment_length * 2) || (travel_time > INFINITY) || nav_fail;
+      if (role == 1) nav_fail = (travel_dist > sb.seg_len2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
       // is_within_simu_time_limit on the test ship's clock (check_condition.py:206-213)
       if (role == 0 && s.time > P.sim_time) my_flags |= 16;
       if (MODE == MODE_STEP && role == 1 && stage == 0) {
         // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
         const double rn = s.north - s.wn, re = s.east - s.we;
-        if ((rn * rn + re * re) < G.roa * G.roa) my_flags |= 32;
+        if ((rn * rn + re * re) < sb.roa2) my_flags |= 32;
       }
       if (IS_RL) {
         const double gd = map_distance(mp, s.north, s.east);
@@ -1392,7 +1443,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       const float o0 = (float)s.north, o1 = (float)s.east;
       float o2, o3 = 0.f, o4 = 0.f;
       if (last_stop_branch) { o2 = (float)s.yaw; o3 = 0.0f; o4 = (float)s.e_ct; }
-      else if (role == 1 && IS_IW) { o2 = (float)s.yaw; o3 = (float)u_pre; o4 = (float)s.e_ct; }
+      else if (role == 1 && IS_IW) { o2 = (float)s.yaw; o3 = (float)scratch.u_pre; o4 = (float)s.e_ct; }
       else { o2 = (float)s.e_ct; }
       const float t0 = __shfl_xor_sync(FULL_MASK, o0, 1);
       const float t1 = __shfl_xor_sync(FULL_MASK, o1, 1);
@@ -1417,8 +1468,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
           ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
           ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
-          ef[SHIPENV_EF_LOG_NORTH * B + env] = log_n;
-          ef[SHIPENV_EF_LOG_EAST * B + env] = log_e;
+          ef[SHIPENV_EF_LOG_NORTH * B + env] = scratch.log_n;
+          ef[SHIPENV_EF_LOG_EAST * B + env] = scratch.log_e;
           if (SBMPC) {
             ef[SHIPENV_EF_SB_P_LAST * B + env] = sb_p_last;
             ef[SHIPENV_EF_SB_CHI_LAST * B + env] = sb_chi_last;
