@@ -266,7 +266,7 @@ int build_grid(shipenv* h) {
   if (h->edges_dev) cudaFree(h->edges_dev);
   CUDA_TRY(cudaMalloc(&h->edges_dev, edges.size() * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemcpy(h->edges_dev, edges.data(), edges.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
-  h->grid = SenvGrid{h->grid_dev, h->edges_dev, p.map_min_e, p.map_min_n, 1.0 / cell, nx, ny};
+  h->grid = SenvGrid{h->grid_dev, h->edges_dev, p.map_min_e, p.map_min_n, 1.0 / cell, (double)nx, (double)ny, nx, ny};
   return SHIPENV_OK;
 }
 
@@ -669,11 +669,11 @@ int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long lo
     return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
   CUDA_TRY(cudaSetDevice(device));
   unsigned long long* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, 8 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(dev, 0, 8 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&dev, 12 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(dev, 0, 12 * sizeof(unsigned long long)));
   CUDA_TRY(senv_fast::launch_math_selftest(n, seed, dev, nullptr));
-  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 4, nullptr));
-  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 6, nullptr));
+  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   cudaFree(dev);
   return SHIPENV_OK;
 }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void load_segment_points(const Route& rt, int n_iw, S
 // and extra spills cost 1-2 %; see profiles/r01_ncu_summary.md part 2.)
 __device__ __forceinline__ double3 segment_bearing(double dx, double dy) {
   double3 out;
-  out.x = atan2(dy, dx);
+  out.x = senv_atan2(dy, dx);
   senv_sincos(out.x, &out.y, &out.z);
   return out;                                                // by value: alpha, sin, cos stay in registers
 }
@@ -358,7 +358,7 @@ __device__ __forceinline__ unsigned map_cell_masks(const MapView& mp, double n_p
   const double fx = (e_pos - mp.grid.e0) * mp.grid.inv_cell;
   const double fy = (n_pos - mp.grid.n0) * mp.grid.inv_cell;
   // outside the grid (or NaN): fall back to every polygon
-  if (!(fx >= 0.0 && fy >= 0.0 && fx < (double)mp.grid.nx && fy < (double)mp.grid.ny)) return all | (all << 16);
+  if (!(fx >= 0.0 && fy >= 0.0 && fx < mp.grid.nx_f && fy < mp.grid.ny_f)) return all | (all << 16);
   return __ldg(mp.grid.cells + (int)fy * mp.grid.nx + (int)fx);
 }
 
@@ -403,7 +403,7 @@ __device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, 
   {
     const double fx = (e_pos - mp.grid.e0) * mp.grid.inv_cell;
     const double fy = (n_pos - mp.grid.n0) * mp.grid.inv_cell;
-    if (!(fx >= 0.0 && fy >= 0.0 && fx < (double)mp.grid.nx && fy < (double)mp.grid.ny)) {
+    if (!(fx >= 0.0 && fy >= 0.0 && fx < mp.grid.nx_f && fy < mp.grid.ny_f)) {
       // outside the grid (or NaN): every segment
       const int nv = mp.start[mp.n_poly];
       m0 = (nv >= 64) ? ~0ull : ((1ull << nv) - 1ull);
@@ -1030,15 +1030,22 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   __shared__ SharedBlock sb_static;
   stage_params(sb_static, dv.params);
   const int lane = (int)(threadIdx.x & 31);
-  const int role = (int)(threadIdx.x & 1);
+  const int role_tid = (int)(threadIdx.x & 1);
   // The shared-memory addresses of the parameter block and of this lane's ship parameters are held in two
   // registers the compiler cannot rematerialise: left alone it recomputed them five times per simulator step
   // (S2R SR_CgaCtaId + S2R SR_TID.X + LEA + LOP3 + IMAD each time: 30 of the loop's 545 instructions, with the
   // S2R latency in front of the parameter loads that follow).  Measured +5.7 % (colav_iw) / +8.5 % (rl).  Doing the
   // same to `role` costs more in spills than the S2R + LOP3 it saves (measured: no gain).
   unsigned sb_addr = (unsigned)__cvta_generic_to_shared(&sb_static);
-  unsigned p_addr = (unsigned)__cvta_generic_to_shared(&sb_static.p.ship[role]);
+  unsigned p_addr = (unsigned)__cvta_generic_to_shared(&sb_static.p.ship[role_tid]);
   asm volatile("" : "+r"(sb_addr), "+r"(p_addr));
+#ifdef SENV_ROLE_FROM_TID
+  const int role = role_tid;
+#else
+  // the role, where it is needed again, from those two registers (a subtraction and a compare) rather than from
+  // S2R SR_TID.X, whose latency sat in front of every role-dependent select
+  const int role = (p_addr - sb_addr) != (unsigned)offsetof(SharedBlock, p.ship[0]) ? 1 : 0;
+#endif
   SharedBlock& sb = *reinterpret_cast<SharedBlock*>(__cvta_shared_to_generic(sb_addr));
   const ShipEnvParams& G = sb.p;
   const ShipEnvShipParams& P = *reinterpret_cast<const ShipEnvShipParams*>(__cvta_shared_to_generic(p_addr));
@@ -1297,8 +1304,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         // RewardDesign3/4 with per-role constants, one exp() call site for both roles
         const double g_scale = role == 0 ? 175000.0 : 50000.0;
         const double n_tol = role == 0 ? 3000.0 : 500.0, n_scale = role == 0 ? 1250000.0 : 12500.0;
-        if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : exp(-(gd * gd) / g_scale);
-        rb = (aect < n_tol) ? exp(-((aect - n_tol) * (aect - n_tol)) / n_scale) : 1.0;
+        if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : senv_exp(-(gd * gd) / g_scale);
+        rb = (aect < n_tol) ? senv_exp(-((aect - n_tol) * (aect - n_tol)) / n_scale) : 1.0;
         if (role == 1) { ra = -ra; rb = -rb; }
       }
     }
@@ -1325,15 +1332,15 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       // partner when the environment is stored).
       double r_total = 0.0;
       if (IS_RL) {
-        const double distance = sqrt(d2);
+        const double distance = SENV_SQRT(d2);
         double r1 = 0.0;
         if (distance < 10000.0) {
-          const double phi = atan2(dy, dx);
+          const double phi = senv_atan2(dy, dx);
           double beta = phi - s.yaw;
           beta = py_mod(beta + kPi, 2 * kPi) - kPi;
           const bool overtaking = !(fabs(beta) < 15.0 * (kPi / 180.0)) && (fabs(beta) > 165.0 * (kPi / 180.0));
           // head-on or crossing -> RewardDesign4(target 0, 2e8); the "overtake" branch is dead code
-          if (!overtaking) r1 = (distance < 0.0) ? 1.0 : exp(-(distance * distance) / 200000000.0);
+          if (!overtaking) r1 = (distance < 0.0) ? 1.0 : senv_exp(-(distance * distance) / 200000000.0);
         }
         r_total = ((((r1 + ra) + rb) + p_ra) + p_rb) / 5;               // test terms, then obstacle terms
       }

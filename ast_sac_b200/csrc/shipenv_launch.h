@@ -19,6 +19,7 @@ struct SenvGrid {
   // the cell.  edges[2*c] = segments 0..63, edges[2*c+1] = segments 64..127.
   const unsigned long long* edges;
   double e0, n0, inv_cell;
+  double nx_f, ny_f;   // nx, ny as doubles (the bounds test of the cell lookup runs at every simulator step)
   int nx, ny;
 };
 
