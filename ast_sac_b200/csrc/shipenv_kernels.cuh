@@ -696,6 +696,9 @@ __device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P)
   return *reinterpret_cast<const Derived*>(reinterpret_cast<const char*>(&P) + kOffset);
 }
 
+// with_routes = false leaves out the segment-bearing tables (64 atan2 + sincos per CTA): the step() prologue, one
+// short CTA per 128 environments, does not read them
+template <bool with_routes = true>
 __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
   unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sb.p);
@@ -723,7 +726,7 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     D.hz_min_e = sb.p.map_min_e + margin; D.hz_max_e = sb.p.map_max_e - margin;
     if (threadIdx.x == 0) { sb.roa2 = sb.p.roa * sb.p.roa; sb.seg_len2 = sb.p.ab_segment_length * 2; }
   }
-  for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
+  for (int i = threadIdx.x; with_routes && i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
     const int r = i / SHIPENV_MAX_WP, k = i % SHIPENV_MAX_WP;
     const ShipEnvShipParams& P = sb.p.ship[r];
     if (k >= 1 && k < P.n_wp) {
@@ -760,49 +763,59 @@ __device__ __forceinline__ int log_begin(const DevView& dv, long long env, long 
   return (dv.log_f64 && env < dv.log_envs) ? dv.log_count[sidx] : -1;
 }
 
+// The rows of ship_f64 are walked with one pointer bumped by the row stride (two integer instructions per row);
+// indexing every row as f[ROW * n_ships + sidx] cost four to five instructions of 64-bit address arithmetic per
+// access, and these loads / stores run for a single lane pair of the warp when it changes environments.
+static_assert(SHIPENV_SF_NORTH == 0 && SHIPENV_SF_EAST == 1 && SHIPENV_SF_YAW == 2 && SHIPENV_SF_U == 3 &&
+              SHIPENV_SF_V == 4 && SHIPENV_SF_R == 5 && SHIPENV_SF_OMEGA == 6 && SHIPENV_SF_TIME == 7 &&
+              SHIPENV_SF_E_CT == 8 && SHIPENV_SF_E_CT_INT == 9 && SHIPENV_SF_HDG_ERR_I == 10 &&
+              SHIPENV_SF_HDG_PREV_ERR == 11 && SHIPENV_SF_SPD_ERR_I == 12 && SHIPENV_SF_SPD_AUX == 13 &&
+              SHIPENV_SF_SEG_ALPHA == 14 && SHIPENV_SF_SEG_SIN == 15 && SHIPENV_SF_SEG_COS == 16,
+              "load_ship / store_ship walk the rows of ship_f64 in this order");
+
 __device__ __forceinline__ void load_ship(const DevView& dv, long long n_ships, long long sidx, Ship& s) {
-  const double* f = dv.buf.ship_f64;
-  s.alpha = f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx];
-  s.sin_a = f[SHIPENV_SF_SEG_SIN * n_ships + sidx];
-  s.cos_a = f[SHIPENV_SF_SEG_COS * n_ships + sidx];
-  s.north = f[SHIPENV_SF_NORTH * n_ships + sidx];
-  s.east = f[SHIPENV_SF_EAST * n_ships + sidx];
-  s.yaw = f[SHIPENV_SF_YAW * n_ships + sidx];
-  s.u = f[SHIPENV_SF_U * n_ships + sidx];
-  s.v = f[SHIPENV_SF_V * n_ships + sidx];
-  s.r = f[SHIPENV_SF_R * n_ships + sidx];
-  s.omega = f[SHIPENV_SF_OMEGA * n_ships + sidx];
-  s.time = f[SHIPENV_SF_TIME * n_ships + sidx];
-  s.e_ct = f[SHIPENV_SF_E_CT * n_ships + sidx];
-  s.e_ct_int = f[SHIPENV_SF_E_CT_INT * n_ships + sidx];
-  s.hdg_err_i = f[SHIPENV_SF_HDG_ERR_I * n_ships + sidx];
-  s.hdg_prev_err = f[SHIPENV_SF_HDG_PREV_ERR * n_ships + sidx];
-  s.spd_err_i = f[SHIPENV_SF_SPD_ERR_I * n_ships + sidx];
-  s.spd_aux = f[SHIPENV_SF_SPD_AUX * n_ships + sidx];
+  const double* p = dv.buf.ship_f64 + sidx;
+  s.north = *p; p += n_ships;
+  s.east = *p; p += n_ships;
+  s.yaw = *p; p += n_ships;
+  s.u = *p; p += n_ships;
+  s.v = *p; p += n_ships;
+  s.r = *p; p += n_ships;
+  s.omega = *p; p += n_ships;
+  s.time = *p; p += n_ships;
+  s.e_ct = *p; p += n_ships;
+  s.e_ct_int = *p; p += n_ships;
+  s.hdg_err_i = *p; p += n_ships;
+  s.hdg_prev_err = *p; p += n_ships;
+  s.spd_err_i = *p; p += n_ships;
+  s.spd_aux = *p; p += n_ships;
+  s.alpha = *p; p += n_ships;
+  s.sin_a = *p; p += n_ships;
+  s.cos_a = *p;
   const int packed = dv.buf.ship_i32[sidx];
   s.k = packed & 0xff;
   s.stop = (packed >> 8) & 1;
 }
 
 __device__ __forceinline__ void store_ship(const DevView& dv, long long n_ships, long long sidx, const Ship& s) {
-  double* f = dv.buf.ship_f64;
-  f[SHIPENV_SF_NORTH * n_ships + sidx] = s.north;
-  f[SHIPENV_SF_EAST * n_ships + sidx] = s.east;
-  f[SHIPENV_SF_YAW * n_ships + sidx] = s.yaw;
-  f[SHIPENV_SF_U * n_ships + sidx] = s.u;
-  f[SHIPENV_SF_V * n_ships + sidx] = s.v;
-  f[SHIPENV_SF_R * n_ships + sidx] = s.r;
-  f[SHIPENV_SF_OMEGA * n_ships + sidx] = s.omega;
-  f[SHIPENV_SF_TIME * n_ships + sidx] = s.time;
-  f[SHIPENV_SF_E_CT * n_ships + sidx] = s.e_ct;
-  f[SHIPENV_SF_E_CT_INT * n_ships + sidx] = s.e_ct_int;
-  f[SHIPENV_SF_HDG_ERR_I * n_ships + sidx] = s.hdg_err_i;
-  f[SHIPENV_SF_HDG_PREV_ERR * n_ships + sidx] = s.hdg_prev_err;
-  f[SHIPENV_SF_SPD_ERR_I * n_ships + sidx] = s.spd_err_i;
-  f[SHIPENV_SF_SPD_AUX * n_ships + sidx] = s.spd_aux;
-  f[SHIPENV_SF_SEG_ALPHA * n_ships + sidx] = s.alpha;
-  f[SHIPENV_SF_SEG_SIN * n_ships + sidx] = s.sin_a;
-  f[SHIPENV_SF_SEG_COS * n_ships + sidx] = s.cos_a;
+  double* p = dv.buf.ship_f64 + sidx;
+  *p = s.north; p += n_ships;
+  *p = s.east; p += n_ships;
+  *p = s.yaw; p += n_ships;
+  *p = s.u; p += n_ships;
+  *p = s.v; p += n_ships;
+  *p = s.r; p += n_ships;
+  *p = s.omega; p += n_ships;
+  *p = s.time; p += n_ships;
+  *p = s.e_ct; p += n_ships;
+  *p = s.e_ct_int; p += n_ships;
+  *p = s.hdg_err_i; p += n_ships;
+  *p = s.hdg_prev_err; p += n_ships;
+  *p = s.spd_err_i; p += n_ships;
+  *p = s.spd_aux; p += n_ships;
+  *p = s.alpha; p += n_ships;
+  *p = s.sin_a; p += n_ships;
+  *p = s.cos_a;
   dv.buf.ship_i32[sidx] = (s.k & 0xff) | (s.stop << 8);
 }
 
@@ -926,7 +939,7 @@ template <int ENVKIND>
 __global__ void __launch_bounds__(128)
 k_prologue(DevView dv, const double* __restrict__ actions) {
   __shared__ SharedBlock sb;
-  stage_params(sb, dv.params);
+  stage_params<false>(sb, dv.params);
   const ShipEnvParams& G = sb.p;
   const long long B = dv.num_envs;
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1123,23 +1136,29 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     if (lstate == LS_LOAD) {
       const long long sidx = 2 * env + role;
       load_ship(dv, n_ships, sidx, s);
-      const double* ef = dv.buf.env_f64;
-      travel_dist = ef[SHIPENV_EF_TRAVEL_DIST * B + env];
-      travel_time = ef[SHIPENV_EF_TRAVEL_TIME * B + env];
-      acc_reward = ef[SHIPENV_EF_ACC_REWARD * B + env];
       {
-        const double log_n = ef[SHIPENV_EF_LOG_NORTH * B + env], log_e = ef[SHIPENV_EF_LOG_EAST * B + env];
+        // rows of env_f64 / env_i32 with a bumped pointer (see load_ship)
+        static_assert(SHIPENV_EF_TRAVEL_DIST == 0 && SHIPENV_EF_TRAVEL_TIME == 1 && SHIPENV_EF_ACC_REWARD == 2 &&
+                      SHIPENV_EF_LOG_NORTH == 5 && SHIPENV_EF_LOG_EAST == 6 && SHIPENV_EF_SB_P_LAST == 7 &&
+                      SHIPENV_EF_SB_CHI_LAST == 8 && SHIPENV_EI_SAMPLING_COUNT == 0 && SHIPENV_EI_FLAGS == 2,
+                      "row order of env_f64 / env_i32");
+        const double* ef = dv.buf.env_f64 + env;
+        travel_dist = *ef; ef += B;
+        travel_time = *ef; ef += B;
+        acc_reward = *ef; ef += 3 * B;
+        const double log_n = *ef; ef += B;
+        const double log_e = *ef; ef += B;
         scratch.log_n = log_n; scratch.log_e = log_e; scratch.u_pre = 0.0;
         const double tn = s.north - log_n, te = s.east - log_e;
         pending_dist = SENV_SQRT(tn * tn + te * te);
+        if (SBMPC) {
+          sb_p_last = *ef; ef += B;
+          sb_chi_last = *ef;
+        }
+        const int* ei = dv.buf.env_i32 + env;
+        sampling_count = *ei; ei += 2 * B;
+        flags = *ei;
       }
-      if (SBMPC) {
-        sb_p_last = ef[SHIPENV_EF_SB_P_LAST * B + env];
-        sb_chi_last = ef[SHIPENV_EF_SB_CHI_LAST * B + env];
-      }
-      const int* ei = dv.buf.env_i32;
-      sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
-      flags = ei[SHIPENV_EI_FLAGS * B + env];
       if (G.collav == SHIPENV_COLLAV_SIMPLE) {
         ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
         ps_on = dv.buf.prev_f32[2 * B + env]; ps_oe = dv.buf.prev_f32[3 * B + env];
@@ -1471,15 +1490,15 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
             orow[1] = IS_IW ? make_float4(o1, o2, o3, o4) : make_float4(o1, o2, 0.f, 0.f);
             ei[SHIPENV_EI_SNAPSHOT_INFO * B + env] = out_info & ~SHIPENV_INFO_DONE;     // results snapshot
           }
-          double* ef = dv.buf.env_f64;
-          ef[SHIPENV_EF_TRAVEL_DIST * B + env] = travel_dist;
-          ef[SHIPENV_EF_TRAVEL_TIME * B + env] = travel_time;
-          ef[SHIPENV_EF_ACC_REWARD * B + env] = acc_reward;
-          ef[SHIPENV_EF_LOG_NORTH * B + env] = scratch.log_n;
-          ef[SHIPENV_EF_LOG_EAST * B + env] = scratch.log_e;
+          double* ef = dv.buf.env_f64 + env;
+          *ef = travel_dist; ef += B;
+          *ef = travel_time; ef += B;
+          *ef = acc_reward; ef += 3 * B;
+          *ef = scratch.log_n; ef += B;
+          *ef = scratch.log_e; ef += B;
           if (SBMPC) {
-            ef[SHIPENV_EF_SB_P_LAST * B + env] = sb_p_last;
-            ef[SHIPENV_EF_SB_CHI_LAST * B + env] = sb_chi_last;
+            *ef = sb_p_last; ef += B;
+            *ef = sb_chi_last;
           }
           ei[SHIPENV_EI_FLAGS * B + env] = flags;
           if (G.collav == SHIPENV_COLLAV_SIMPLE) {
