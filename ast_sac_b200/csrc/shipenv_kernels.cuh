@@ -166,10 +166,15 @@ __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship&
 
 // heading_offset / speed_factor: SBMPC's course offset (already negated, "pos == clockwise in sim",
 // env.py:394) and speed factor; (-0.0, 1.0) without SBMPC.
-template <int MODEL>
+// `hook(north, east)` is called with the ship's new position as soon as the kinematics have it -- the same
+// expressions as the Euler update at the end of the step -- so the caller can start loads that depend on it (the
+// env kernel's culling-grid lookup) before the ~100 instructions of kinetics instead of after them.
+struct NoStepHook { __device__ __forceinline__ void operator()(double, double) const {} };
+
+template <int MODEL, class Hook = NoStepHook>
 __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
                                           bool collav_hit, double collav_bias, double heading_offset,
-                                          double speed_factor, double* log_row = nullptr) {
+                                          double speed_factor, double* log_row = nullptr, Hook hook = Hook()) {
   // --- NavigationSystem.next_wpt
   {
     const double dn = s.wn - s.north, de = s.we - s.east;
@@ -247,6 +252,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double u = s.u, v = s.v, r = s.r;
   const double d_north = cpsi * u + (-spsi) * v;
   const double d_east = spsi * u + cpsi * v;
+  hook(s.north + d_north * P.dt, s.east + d_east * P.dt);
   // --- machinery
   double thrust, d_omega = 0.0;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
@@ -357,9 +363,12 @@ __device__ __forceinline__ unsigned map_cell_masks(const MapView& mp, double n_p
   const unsigned all = (mp.n_poly >= 16) ? 0xffffu : ((1u << mp.n_poly) - 1u);
   const double fx = (e_pos - mp.grid.e0) * mp.grid.inv_cell;
   const double fy = (n_pos - mp.grid.n0) * mp.grid.inv_cell;
-  // outside the grid (or NaN): fall back to every polygon
-  if (!(fx >= 0.0 && fy >= 0.0 && fx < mp.grid.nx_f && fy < mp.grid.ny_f)) return all | (all << 16);
-  return __ldg(mp.grid.cells + (int)fy * mp.grid.nx + (int)fx);
+  // outside the grid (or NaN): fall back to every polygon.  No branch: the load always happens (cell 0 then), so
+  // it can be issued early and overlap other work.
+  const bool inside = ((int)(fx >= 0.0) & (int)(fy >= 0.0) & (int)(fx < mp.grid.nx_f) & (int)(fy < mp.grid.ny_f)) != 0;
+  const int ix = (int)(inside ? fx : 0.0), iy = (int)(inside ? fy : 0.0);
+  const unsigned m = __ldg(mp.grid.cells + iy * mp.grid.nx + ix);
+  return inside ? m : (all | (all << 16));
 }
 
 // Polygon.contains(Point(x, y)) for one polygon: even-odd crossing rule
@@ -1196,6 +1205,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     // side, except under SBMPC in the NonIW env, where obs_step's SBMPC call reads the state the ship under
     // test has just integrated to (run_colav env.py:502-527): two phases there.
     constexpr int N_PHASE = (SBMPC && !IS_IW) ? 2 : 1;
+    unsigned cell = 0;          // culling-grid masks of the cell the ship is in after this step (set by every running lane)
 #pragma unroll 1
     for (int phase = 0; phase < N_PHASE; ++phase) {
     const bool stepping = running && (N_PHASE == 1 || role == phase);
@@ -1259,6 +1269,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         s.time = s.time + dt;
         s.time = s.time + dt;
         last_stop_branch = true;
+        cell = map_cell_masks(mp, s.north, s.east);
       } else {
         scratch.u_pre = s.u;
         last_stop_branch = false;
@@ -1270,7 +1281,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         }
         const double pre_n = s.north, pre_e = s.east;
         ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
-                         log_next_row(dv, 2 * env + role, tlog_n));
+                         log_next_row(dv, 2 * env + role, tlog_n),
+                         [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); });
         if (role == 1 && IS_IW) {
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
@@ -1295,7 +1307,6 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     double ra = 0.0, rb = 0.0;
     if (running) {
       const double len = P.l_ship;
-      const unsigned cell = map_cell_masks(mp, s.north, s.east);
       const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
       // (four comparisons combined without short-circuit branches)
       const Derived& D = derived_of(P);
