@@ -139,10 +139,13 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   // previous launch's count (copied to pinned memory without a sync, so it may lag by a launch).
   if (mode == 0) {
     // step(action): the per-environment prologue first, at full width (csrc/shipenv_kernels.cuh k_prologue)
+    // (it also restarts the work-queue counters of the env kernel)
     cudaError_t pe = (h->params.math_mode == SHIPENV_MATH_FAST)
-                         ? senv_fast::launch_prologue(view(h), h->params.env_kind, actions, st)
-                         : senv_strict::launch_prologue(view(h), h->params.env_kind, actions, st);
+                         ? senv_fast::launch_prologue(view(h), h->params.env_kind, actions, h->queue_dev, st)
+                         : senv_strict::launch_prologue(view(h), h->params.env_kind, actions, h->queue_dev, st);
     if (pe != cudaSuccess) return fail(SHIPENV_E_CUDA, "prologue kernel launch: %s", cudaGetErrorString(pe));
+  } else {
+    CUDA_TRY(cudaMemsetAsync(h->queue_dev, 0, 2 * sizeof(unsigned long long), st));
   }
   int persistent = h->persist_mode;
   if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
@@ -152,14 +155,13 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
       if (cudaEventSynchronize(h->ev_k1) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev_k0, h->ev_k1) == cudaSuccess)
         h->kernel_ms_sum += ms;
     }
-    CUDA_TRY(cudaMemsetAsync(h->queue_dev, 0, 2 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(h->ev_k0, st));
   }
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
                       ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                              h->sm_count, persistent, h->time_kernels ? 0 : 1, st)
+                                              h->sm_count, persistent, 0, st)
                       : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                                h->sm_count, persistent, h->time_kernels ? 0 : 1, st);
+                                                h->sm_count, persistent, 0, st);
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
   if (h->time_kernels) {
     CUDA_TRY(cudaEventRecord(h->ev_k1, st));

@@ -373,9 +373,12 @@ __device__ __forceinline__ unsigned map_cell_masks(const MapView& mp, double n_p
 
 // Polygon.contains(Point(x, y)) for one polygon: even-odd crossing rule
 __device__ __forceinline__ bool poly_contains(const MapView& mp, int p, double x, double y) {
-  const double* bb = mp.bbox + 4 * p;
-  // a point outside the polygon's bounding box crosses an even number of edges (exact skip)
-  if (x < bb[0] || x > bb[1] || y < bb[2] || y > bb[3]) return false;
+  // a point outside the polygon's bounding box crosses an even number of edges (exact skip; the step() prologue
+  // stages no bounding boxes and walks the edges)
+  if (mp.bbox) {
+    const double* bb = mp.bbox + 4 * p;
+    if (x < bb[0] || x > bb[1] || y < bb[2] || y > bb[3]) return false;
+  }
   const int a = mp.start[p], b = mp.start[p + 1];
   bool inside = false;
   double xj = mp.ve[b - 1], yj = mp.vn[b - 1];
@@ -705,8 +708,9 @@ __device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P)
   return *reinterpret_cast<const Derived*>(reinterpret_cast<const char*>(&P) + kOffset);
 }
 
-// with_routes = false leaves out the segment-bearing tables (64 atan2 + sincos per CTA): the step() prologue, one
-// short CTA per 128 environments, does not read them
+// with_routes = false copies the parameter block only and leaves out the bounding boxes, the per-ship derived
+// constants and the segment-bearing tables (64 atan2 + sincos per CTA): the step() prologue, one short CTA per 128
+// environments, reads none of them
 template <bool with_routes = true>
 __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
@@ -714,6 +718,7 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
   constexpr int words = sizeof(ShipEnvParams) / 8;
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   __syncthreads();
+  if (!with_routes) return;
   for (int p = threadIdx.x; p < sb.p.n_poly; p += blockDim.x) {
     double mne = INFINITY, mxe = -INFINITY, mnn = INFINITY, mxn = -INFINITY;
 #pragma unroll 1
@@ -735,7 +740,7 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     D.hz_min_e = sb.p.map_min_e + margin; D.hz_max_e = sb.p.map_max_e - margin;
     if (threadIdx.x == 0) { sb.roa2 = sb.p.roa * sb.p.roa; sb.seg_len2 = sb.p.ab_segment_length * 2; }
   }
-  for (int i = threadIdx.x; with_routes && i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
     const int r = i / SHIPENV_MAX_WP, k = i % SHIPENV_MAX_WP;
     const ShipEnvShipParams& P = sb.p.ship[r];
     if (k >= 1 && k < P.n_wp) {
@@ -946,7 +951,9 @@ __global__ void k_init_prev_states(DevView dv) {
 // ------------------------------------------------------------------------------------------------
 template <int ENVKIND>
 __global__ void __launch_bounds__(128)
-k_prologue(DevView dv, const double* __restrict__ actions) {
+k_prologue(DevView dv, const double* __restrict__ actions, unsigned long long* __restrict__ queue) {
+  // the work-queue counters of the k_env launch that follows on the same stream restart at 0
+  if (blockIdx.x == 0 && threadIdx.x < 2) queue[threadIdx.x] = 0ull;
   __shared__ SharedBlock sb;
   stage_params<false>(sb, dv.params);
   const ShipEnvParams& G = sb.p;
@@ -961,7 +968,7 @@ k_prologue(DevView dv, const double* __restrict__ actions) {
   flags &= ~SHIPENV_FLAG_HAVE_IW;
   int sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
   if (sampling_count < G.max_sampling_frequency) {
-    const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
+    const MapView mp{G.vert_e, G.vert_n, G.poly_start, nullptr, nullptr, G.n_poly, dv.grid};
     const double a = actions[env];
     sampling_count += 1;
     // get_intermediate_waypoints (env.py:198-236)
@@ -1634,10 +1641,11 @@ static void launch_env_kind(const SenvView& v, int env_kind, const double* actio
   }
 }
 
-cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, cudaStream_t st) {
+cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, unsigned long long* queue,
+                            cudaStream_t st) {
   const int grid = (int)((v.num_envs + kBlock - 1) / kBlock);
-  if (env_kind == SHIPENV_ENV_RL) k_prologue<SHIPENV_ENV_RL><<<grid, kBlock, 0, st>>>(v, actions);
-  else k_prologue<SHIPENV_ENV_COLAV_IW><<<grid, kBlock, 0, st>>>(v, actions);
+  if (env_kind == SHIPENV_ENV_RL) k_prologue<SHIPENV_ENV_RL><<<grid, kBlock, 0, st>>>(v, actions, queue);
+  else k_prologue<SHIPENV_ENV_COLAV_IW><<<grid, kBlock, 0, st>>>(v, actions, queue);
   return cudaGetLastError();
 }
 

@@ -40,7 +40,8 @@ struct SenvView {
   cudaError_t launch_reset(const SenvView& v, int model, const uint8_t* mask, const double* init, int do_init, \
                            int reinit, cudaStream_t st);                                                       \
   cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st);                                            \
-  cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions, cudaStream_t st);        \
+  cudaError_t launch_prologue(const SenvView& v, int env_kind, const double* actions,                          \
+                              unsigned long long* queue, cudaStream_t st);                                     \
   cudaError_t launch_env(const SenvView& v, int model, int env_kind, int mode, const double* actions, int k,   \
                          unsigned long long* queue, int sm_count, int persistent, int clear_queue,           \
                          cudaStream_t st);                                                                     \

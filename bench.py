@@ -217,7 +217,7 @@ def run_b200(a, rank, local_rank, world):
     B = a.envs
     args, assets, m, actions_cpu, init_cpu = make_inputs(a.workload, B, rank, a.collav)
     init_dev = init_cpu.to(dev)
-    actions_dev = actions_cpu.to(dev)
+    actions_dev = actions_cpu.to(dev).t().contiguous()                  # [9, B]: one contiguous row per step() call
     actions_host = np.ascontiguousarray(actions_cpu.numpy().T)          # [9, B] rows for the host API
     if a.workload == "rl":
         env = S.MultiShipRLEnv(assets=assets, map=m, args=args, num_envs=B, device=dev, init_states=init_dev,
@@ -249,7 +249,7 @@ def run_b200(a, rank, local_rank, world):
             if j < 0:
                 env.reset()
             else:
-                env.step(actions_dev[:, j])
+                env.step(actions_dev[j])
             if events is not None:
                 e.record(stream)
                 pairs.append((s, e))
