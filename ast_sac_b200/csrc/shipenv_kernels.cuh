@@ -1104,11 +1104,12 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   // instead of the previous position, which would have to be rotated through registers at every step.  The
   // previous position itself (LOG_NORTH / LOG_EAST rows of env_f64) and the surge speed before the integration
   // (obs[6]) are only needed when the environment is stored: they are written to a per-lane shared-memory slot.
-  struct LaneScratch { double log_n, log_e, u_pre, pad; };
-  __shared__ LaneScratch lane_scratch[128];
-  unsigned scratch_addr = (unsigned)__cvta_generic_to_shared(&lane_scratch[threadIdx.x]);
+  // ([field][thread]: a warp's 8-byte stores of one field are conflict-free)
+  __shared__ double lane_scratch[3][128];
+  unsigned scratch_addr = (unsigned)__cvta_generic_to_shared(&lane_scratch[0][threadIdx.x]);
   asm volatile("" : "+r"(scratch_addr));
-  LaneScratch& scratch = *reinterpret_cast<LaneScratch*>(__cvta_shared_to_generic(scratch_addr));
+  double* const scratch_base = reinterpret_cast<double*>(__cvta_shared_to_generic(scratch_addr));
+  struct { double& log_n; double& log_e; double& u_pre; } scratch{scratch_base[0], scratch_base[128], scratch_base[256]};
   double pending_dist = 0.0;
   int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
   double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)

@@ -40,10 +40,10 @@ N_RL_STEPS = 9
 #    ncu capture under profiles/ (includes the CUDA math library's sin/cos/atan2/exp internals and
 #    the map-geometry tests); filled in from profiles/r01_ncu_summary.md.
 FLOP_ALGO = {"colav_iw": 370.0 + 26.0, "rl": 450.0 + 31.0}
-FLOP_EXEC = {"colav_iw": 602.0, "rl": 1180.0}     # profiles/r01_ncu_summary.md part 2, section 2 (fast build)
+FLOP_EXEC = {"colav_iw": 567.0, "rl": 1150.0}     # profiles/r01_ncu_summary.md part 4, section 2 (fast build)
 # DRAM bytes (read + written) of one k_env<MODE_STEP> launch over 1e5 environments, from the ncu --set full
 # capture summarised in profiles/r01_ncu_summary.md part 2 (dram__bytes_read.sum + dram__bytes_write.sum)
-TRAFFIC_PER_LAUNCH_1E5 = {"colav_iw": 37.1e6, "rl": 38.6e6}
+TRAFFIC_PER_LAUNCH_1E5 = {"colav_iw": 41.0e6, "rl": 40.7e6}
 # HBM bytes per env-step when every simulator step is its own launch (K = 1): DESIGN.md section 4
 BYTES_K1 = 2 * 2 * (17 * 8 + 4) + 2 * (5 * 8 + 2 * 4) + 32 + 8 + 4 + 4     # ship rows r+w, env rows r+w, outputs = 704 B (ABI v5)
 
@@ -101,37 +101,55 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _init(self):
+        """NVML handle and the reason-bit names; done before the timed region starts (nvmlInit takes ~100 ms)."""
+        import pynvml as nv
+        nv.nvmlInit()
+        self._nv = nv
+        self._h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        self._names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+
+    def _sample(self):
+        nv, h = self._nv, self._h
+        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, name in self._names.items():
+            if r & bit:
+                self.reasons.add(name)
+
     def _run(self):
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
-                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
-                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
-            }
             while not self._stop.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                time.sleep(0.05)
-        except Exception as exc:   # NVML missing: record that instead of failing the bench
+                self._sample()
+                time.sleep(0.004)
+        except Exception as exc:
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 
     def start(self):
+        try:
+            self._init()
+        except Exception as exc:   # NVML missing: record that instead of failing the bench
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+            return
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
 
     def stop(self):
+        if self._t:
+            try:
+                self._sample()                   # at least one sample while the GPU is still under load
+            except Exception:
+                pass
         self._stop.set()
         if self._t:
             self._t.join(timeout=2)
