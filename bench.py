@@ -102,7 +102,8 @@ class ClockSampler:
         self._t = None
 
     def _init(self):
-        """NVML handle and the reason-bit names; done before the timed region starts (nvmlInit takes ~100 ms)."""
+        """NVML handle and the reason-bit names; done before the timed region starts (nvmlInit takes ~100 ms).
+        Sampled every 15 ms (every rank samples its own GPU; NVML queries are not free, so the period stays coarse)."""
         import pynvml as nv
         nv.nvmlInit()
         self._nv = nv
@@ -131,7 +132,7 @@ class ClockSampler:
         try:
             while not self._stop.is_set():
                 self._sample()
-                time.sleep(0.004)
+                time.sleep(0.015)
         except Exception as exc:
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
 
