@@ -138,3 +138,27 @@ def test_layout_constants_match_header():
     assert len(re.findall(r"SHIPENV_EF_\w+", ef)) == L.EF_COUNT == len(L.EF)
     lg = re.search(r"SHIPENV_LOG_TIME = 0,(.*?)SHIPENV_LOG_COLS", hdr, re.S).group(1)
     assert 1 + len(re.findall(r"SHIPENV_LOG_\w+", lg)) == len(L.LOG_COLS)
+
+
+def test_batched_info_decodes_lazily_and_like_the_eager_dict():
+    """BatchedInfo (env_info of a batched call): the reference's keys, decoded from the packed info words on first
+    access and cached; a read-only Mapping."""
+    import torch
+    words = torch.tensor([0, 0x3 | L.INFO_TERMINAL | L.INFO_DONE, 0x40 | L.INFO_TEST_STOP,
+                          0x100 | L.INFO_OBS_STOP | L.INFO_TEST_STOP | L.INFO_DONE], dtype=torch.int32)
+    nsub = torch.tensor([5, 7, 0, 9], dtype=torch.int32)
+    info = E.BatchedInfo(words, nsub)
+    assert list(info) == ['events', 'terminal', 'test_ship_stop', 'obs_ship_stop', 'substeps'] and len(info) == 5
+    assert info._cache == {}                                          # nothing decoded yet
+    assert info['events'].tolist() == [0, 0x3, 0x40, 0x100]
+    assert info['terminal'].tolist() == [False, True, False, False]
+    assert info['test_ship_stop'].tolist() == [False, False, True, True]
+    assert info['obs_ship_stop'].tolist() == [False, False, False, True]
+    assert info['substeps'] is nsub
+    assert info['terminal'] is info['terminal']                        # cached
+    assert dict(info).keys() == {'events', 'terminal', 'test_ship_stop', 'obs_ship_stop', 'substeps'}
+    assert info.get('missing') is None
+    with pytest.raises(KeyError):
+        info['missing']
+    with pytest.raises(TypeError):
+        info['terminal'] = 1                                           # Mapping, not MutableMapping
