@@ -555,7 +555,7 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
   const double ob_dx = ((-so) * in.ob_u + co * in.ob_v) * kSbDt;
   const double ob_dy = (co * in.ob_u + so * in.ob_v) * kSbDt;
   const double vo0 = (-so) * in.ob_u + co * in.ob_v, vo1 = co * in.ob_u + so * in.ob_v;   // rot2d, sbmpc.py:312-314
-  const double n_vo = sqrt(vo0 * vo0 + vo1 * vo1);
+  const double n_vo = SENV_SQRT(vo0 * vo0 + vo1 * vo1);
   // own ship: heading psi_d from sample 1 on, wrapped heading and the measured sway speed at sample 0
   const double ud = in.u_d * p_ca, psi_d = in.chi_d + chi_ca;
   double s0, c0, sd, cd;
@@ -573,12 +573,12 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
   // world-frame velocities and what depends only on them: sample 0 (A) and samples >= 1 (B)
   const double vsA0 = (-s0) * ud + c0 * in.os_v, vsA1 = c0 * ud + s0 * in.os_v;
   const double vsB0 = (-sd) * ud + cd * zero, vsB1 = cd * ud + sd * zero;
-  const double n_vsA = sqrt(vsA0 * vsA0 + vsA1 * vsA1), n_vsB = sqrt(vsB0 * vsB0 + vsB1 * vsB1);
+  const double n_vsA = SENV_SQRT(vsA0 * vsA0 + vsA1 * vsA1), n_vsB = SENV_SQRT(vsB0 * vsB0 + vsB1 * vsB1);
   const bool otA = (vsA0 * vo0 + vsA1 * vo1) > cos_ot * n_vsA * n_vo && n_vsA > n_vo;
   const bool otB = (vsB0 * vo0 + vsB1 * vo1) > cos_ot * n_vsB * n_vo && n_vsB > n_vo;
   const double k_coll = 1e-6 * os_l * obs_l;
-  const double nrA = sqrt((vsA0 - vo0) * (vsA0 - vo0) + (vsA1 - vo1) * (vsA1 - vo1));
-  const double nrB = sqrt((vsB0 - vo0) * (vsB0 - vo0) + (vsB1 - vo1) * (vsB1 - vo1));
+  const double nrA = SENV_SQRT((vsA0 - vo0) * (vsA0 - vo0) + (vsA1 - vo1) * (vsA1 - vo1));
+  const double nrB = SENV_SQRT((vsB0 - vo0) * (vsB0 - vo0) + (vsB1 - vo1) * (vsB1 - vo1));
   const double ccA = k_coll * (nrA * nrA), ccB = k_coll * (nrB * nrB);   // K_COLL * |v_s - v_o| ** 2
   // safety distance by the sector the own ship is seen in from the obstacle (sbmpc.py:232-245)
   const double ds_ahead = d_safe + obs_l / 2, ds_behind = 0.5 * d_safe + obs_l / 2, ds_beam = d_safe + obs_w / 2;
@@ -594,7 +594,7 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
   auto sample = [&](double e0, double e1, double t, bool ot, double cc) {
     const double d2 = e0 * e0 + e1 * e1;
     if (!(d2 < far2)) return;
-    const double dist = sqrt(d2);
+    const double dist = SENV_SQRT(d2);
     if (!(dist < d_close)) return;
     bool within;
     if (ot) within = dist < ds_ot;
@@ -616,8 +616,8 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
 #endif
     }
     if (within) {
-      const double q = d_safe / dist;
-      const double R = (1.0 / t) * ((q * q) * (q * q));     // (1 / |t - t0| ** P_) * (d_safe / dist) ** Q_
+      const double q = SENV_DIV(d_safe, dist);
+      const double R = SENV_DIV(1.0, t) * ((q * q) * (q * q));     // (1 / |t - t0| ** P_) * (d_safe / dist) ** Q_
       const double H0 = cc * R + 0.0;                       // + KAPPA_ * mu, KAPPA_ = 0
       if (H0 > H1) H1 = H0;
     }
@@ -640,7 +640,7 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
       const double disc = qb * qb - qa * qc;
       if (disc < 0.0) k_hi = 0;                                // never that close
       else {
-        const double root = sqrt(disc), inv = 1.0 / qa;
+        const double root = SENV_SQRT(disc), inv = SENV_DIV(1.0, qa);
         const double lo = (-qb - root) * inv - 1.0, hi = (-qb + root) * inv + 1.0;
         if (lo > (double)k_lo) k_lo = (lo < 1.0e6) ? (int)lo : kSbSamples;
         if (hi < (double)k_hi) k_hi = (hi > -1.0e6) ? (int)ceil(hi) : 0;
@@ -1238,7 +1238,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       bool active = false;
       if (pair_calls) {
         const double d0 = in.ob_x - in.os_x, d1 = in.ob_y - in.os_y;
-        active = sqrt(d0 * d0 + d1 * d1) < 2000.0;
+        active = SENV_SQRT(d0 * d0 + d1 * d1) < 2000.0;
         if (!active) { sb_p_last = 1.0; sb_chi_last = 0.0; }
       }
       unsigned todo = __ballot_sync(FULL_MASK, caller && active);
