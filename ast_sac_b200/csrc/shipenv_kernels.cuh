@@ -130,12 +130,20 @@ __device__ __forceinline__ double sat(double val, double low, double hi) {   // 
 // parameters only, evaluated once per CTA by stage_params with the same IEEE operations, so the values are the
 // ones the step computed inline).  derived_of(P) finds the block of the ship whose parameters P refers to: the
 // two blocks are laid out in shared memory with the stride of ShipEnvShipParams, at a fixed distance from it.
-struct Derived {
-  double los_r2, los_r99, los_ra2;        // R * R, 0.99 * R (LOS_guidance.py:111-113), ra * ra (:88-92)
+struct alignas(16) Derived {
+  // -- in the order the simulator step reads them (adjacent pairs load as one LDS.128)
+  double los_ra2, los_r2;                 // ra * ra (LOS_guidance.py:88-92), R * R
+  double los_r99, los_limit;              // 0.99 * R (LOS_guidance.py:111-113)
+  double los_ki;
+  double inv_ctrl_dt, ctrl_dt, hdg_kp, hdg_kd, hdg_ki, max_rudder, desired_speed, spd_kp, spd_kd, spd_ki, max_thrust, dt, cur_n, cur_e, c_rudder_v, c_rudder_r, cos_wind_dir, sin_wind_dir, wind_speed;
   double wind_cu, wind_cv, wind_cn;       // -0.3 A_f, -0.42 A_l, -0.096 A_l L (fast build's wind force)
+  double mass, y_dv, x_du, lin_damp_u, ku, lin_damp_v, kv, lin_damp_r, kr, inv_m_u, inv_m_v, inv_m_r;
   double hz_min_n, hz_max_n, hz_min_e, hz_max_e;   // map horizon moved in by half a ship length (check_condition.py:96-119)
+  double l_ship, nav_fail_tol, sim_time;
+  // -- machinery models (detailed / simplified)
+  double kp_ship_speed, ki_ship_speed, max_shaft_speed, kp_shaft_speed, ki_shaft_speed, p_me, p_el, tq_me_max, tq_el_max, d_me, r_me, d_hsg, r_hsg, k_torque, jp, thrust_coeff, dt_shaft, k_thrust, thrust_tau;
 };
-struct DerivedSlot {
+struct alignas(16) DerivedSlot {
   Derived d;
   char pad[sizeof(ShipEnvShipParams) - sizeof(Derived)];
 };
@@ -159,8 +167,8 @@ __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship&
   double delta = SENV_SQRT(R2 - e_ct * e_ct);
   if (!(delta > 1e-6)) delta = 1e-6;
   const double q = SENV_DIV(e_ct, delta);
-  if (fabs(s.e_ct_int + q) <= P.los_limit) s.e_ct_int += q;
-  const double chi_r = senv_atan(-q - s.e_ct_int * P.los_ki);
+  if (fabs(s.e_ct_int + q) <= D.los_limit) s.e_ct_int += q;
+  const double chi_r = senv_atan(-q - s.e_ct_int * D.los_ki);
   return s.alpha + chi_r;
 }
 
@@ -175,10 +183,11 @@ template <int MODEL, class Hook = NoStepHook>
 __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
                                           bool collav_hit, double collav_bias, double heading_offset,
                                           double speed_factor, double* log_row = nullptr, Hook hook = Hook()) {
+  const Derived& H = derived_of(P);   // the step's parameters in reading order (see Derived)
   // --- NavigationSystem.next_wpt
   {
     const double dn = s.wn - s.north, de = s.we - s.east;
-    if (dn * dn + de * de <= derived_of(P).los_ra2) {
+    if (dn * dn + de * de <= H.los_ra2) {
       if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
     }
   }
@@ -189,54 +198,54 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   {
     const double error = (heading_ref + heading_offset) - s.yaw;
 #if SENV_FAST_MATH
-    const double d_error = (error - s.hdg_prev_err) * P.inv_ctrl_dt;
+    const double d_error = (error - s.hdg_prev_err) * H.inv_ctrl_dt;
 #else
-    const double d_error = (error - s.hdg_prev_err) / P.ctrl_dt;
+    const double d_error = (error - s.hdg_prev_err) / H.ctrl_dt;
 #endif
-    const double error_i = s.hdg_err_i + error * P.ctrl_dt;
+    const double error_i = s.hdg_err_i + error * H.ctrl_dt;
     s.hdg_prev_err = error;
     s.hdg_err_i = error_i;
-    const double out = error * P.hdg_kp + d_error * P.hdg_kd + error_i * P.hdg_ki;
-    rudder = sat(-out, -P.max_rudder, P.max_rudder);
+    const double out = error * H.hdg_kp + d_error * H.hdg_kd + error_i * H.hdg_ki;
+    rudder = sat(-out, -H.max_rudder, H.max_rudder);
   }
   // --- speed controller
   double cmd;
-  const double speed_set_point = P.desired_speed * speed_factor;
+  const double speed_set_point = H.desired_speed * speed_factor;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
     const double error = speed_set_point - s.u;
 #if SENV_FAST_MATH
-    const double d_error = (error - s.spd_aux) * P.inv_ctrl_dt;
+    const double d_error = (error - s.spd_aux) * H.inv_ctrl_dt;
 #else
-    const double d_error = (error - s.spd_aux) / P.ctrl_dt;
+    const double d_error = (error - s.spd_aux) / H.ctrl_dt;
 #endif
-    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    const double error_i = s.spd_err_i + error * H.ctrl_dt;
     s.spd_aux = error;
     s.spd_err_i = error_i;
-    const double out = error * P.spd_kp + d_error * P.spd_kd + error_i * P.spd_ki;
-    cmd = sat(out, -P.max_thrust, P.max_thrust);
+    const double out = error * H.spd_kp + d_error * H.spd_kd + error_i * H.spd_ki;
+    cmd = sat(out, -H.max_thrust, H.max_thrust);
   } else if (MODEL == SHIPENV_MODEL_SIMPLIFIED) {
     // ThrottleFromSpeedSetPointSimplifiedPropulsion.throttle (rl_env controllers.py:229-232)
     const double error = speed_set_point - s.u;
-    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    const double error_i = s.spd_err_i + error * H.ctrl_dt;
     s.spd_err_i = error_i;
-    cmd = sat(error * P.kp_ship_speed + error_i * P.ki_ship_speed, 0.0, 1.1);
+    cmd = sat(error * H.kp_ship_speed + error_i * H.ki_ship_speed, 0.0, 1.1);
   } else {
     const double error = speed_set_point - s.u;
-    const double error_i = s.spd_err_i + error * P.ctrl_dt;
+    const double error_i = s.spd_err_i + error * H.ctrl_dt;
     s.spd_err_i = error_i;
-    const double w_d = sat(error * P.kp_ship_speed + error_i * P.ki_ship_speed, 0.0, P.max_shaft_speed);
+    const double w_d = sat(error * H.kp_ship_speed + error_i * H.ki_ship_speed, 0.0, H.max_shaft_speed);
     // measured_shaft_speed = forward_speed (rl_env env.py:397-401)
     const double error2 = w_d - s.u;
-    const double error2_i = s.spd_aux + error2 * P.ctrl_dt;
+    const double error2_i = s.spd_aux + error2 * H.ctrl_dt;
     s.spd_aux = error2_i;
-    cmd = sat(error2 * P.kp_shaft_speed + error2_i * P.ki_shaft_speed, 0.0, 1.1);
+    cmd = sat(error2 * H.kp_shaft_speed + error2_i * H.ki_shaft_speed, 0.0, 1.1);
   }
   // --- collav 'simple' (run_colav env.py:1189-1202, rl_env env.py:405-418)
   if (collav_hit) {
     cmd *= 0.5;
     cmd = (cmd < 0.0) ? 0.0 : ((cmd > 1.1) ? 1.1 : cmd);
     rudder += collav_bias;
-    rudder = (rudder < -P.max_rudder) ? -P.max_rudder : ((rudder > P.max_rudder) ? P.max_rudder : rudder);
+    rudder = (rudder < -H.max_rudder) ? -H.max_rudder : ((rudder > H.max_rudder) ? H.max_rudder : rudder);
   }
   // --- store_simulation_data (ship_model.py:418-429): the row is logged before the integration
   if (log_row) {
@@ -252,7 +261,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double u = s.u, v = s.v, r = s.r;
   const double d_north = cpsi * u + (-spsi) * v;
   const double d_east = spsi * u + cpsi * v;
-  hook(s.north + d_north * P.dt, s.east + d_east * P.dt);
+  hook(s.north + d_north * H.dt, s.east + d_east * H.dt);
   // --- machinery
   double thrust, d_omega = 0.0;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
@@ -260,28 +269,28 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   } else if (MODEL == SHIPENV_MODEL_SIMPLIFIED) {
     // SimplifiedMachineryModel.update_thrust_force (ship_engine.py:508-513); the thrust state feeds the
     // kinetics before it is integrated
-    const double power = cmd * (P.p_me + P.p_el);
+    const double power = cmd * (H.p_me + H.p_el);
     thrust = s.omega;
-    d_omega = (-P.k_thrust * s.omega + power) / P.thrust_tau;
+    d_omega = (-H.k_thrust * s.omega + power) / H.thrust_tau;
   } else {
     const double w = s.omega;
     // (the divisions stay exact in both builds: replacing them by reciprocal multiplications moved the
     //  ill-conditioned detailed model past 1e-9 on one golden episode, rl_dt4_PTO)
-    const double a_me = cmd * P.p_me / (w + 0.1);
-    const double tq_me = (P.tq_me_max < a_me) ? P.tq_me_max : a_me;
-    const double a_el = cmd * P.p_el / (w + 0.1);
-    const double tq_el = (P.tq_el_max < a_el) ? P.tq_el_max : a_el;
-    const double eq_me = (tq_me - P.d_me * w) / P.r_me;
-    const double eq_hsg = (tq_el - P.d_hsg * w) / P.r_hsg;
-    d_omega = (eq_me + eq_hsg - P.k_torque * (w * w)) / P.jp;
-    thrust = P.thrust_coeff * w * fabs(w);
+    const double a_me = cmd * H.p_me / (w + 0.1);
+    const double tq_me = (H.tq_me_max < a_me) ? H.tq_me_max : a_me;
+    const double a_el = cmd * H.p_el / (w + 0.1);
+    const double tq_el = (H.tq_el_max < a_el) ? H.tq_el_max : a_el;
+    const double eq_me = (tq_me - H.d_me * w) / H.r_me;
+    const double eq_hsg = (tq_el - H.d_hsg * w) / H.r_hsg;
+    d_omega = (eq_me + eq_hsg - H.k_torque * (w * w)) / H.jp;
+    thrust = H.thrust_coeff * w * fabs(w);
   }
   // --- current in the body frame, rudder forces
-  const double u_c = cpsi * P.cur_n + spsi * P.cur_e;
-  const double v_c = (-spsi) * P.cur_n + cpsi * P.cur_e;
+  const double u_c = cpsi * H.cur_n + spsi * H.cur_e;
+  const double v_c = (-spsi) * H.cur_n + cpsi * H.cur_e;
   const double u_r = u - u_c, v_r = v - v_c;
-  const double f_rudder_v = -P.c_rudder_v * rudder * (u - u_c);
-  const double f_rudder_r = -P.c_rudder_r * rudder * (u - u_c);
+  const double f_rudder_v = -H.c_rudder_v * rudder * (u - u_c);
+  const double f_rudder_r = -H.c_rudder_r * rudder * (u - u_c);
   // --- wind (get_wind_force, ship_model.py:162-175)
 #if SENV_FAST_MATH
   // u_rw = ws*cos(wd - psi) - u, v_rw = ws*sin(wd - psi) - v with the angle-difference identity;
@@ -289,20 +298,19 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   // sin(2 gamma) = -2 u_rw v_rw/|V|^2, so with q = 0.6 |V|^2:
   //   tau_u = q*(-0.5 cos g)*A_f = -0.3 A_f |V| u_rw,  tau_v = q*(0.7 sin g)*A_l = -0.42 A_l |V| v_rw,
   //   tau_n = q*(0.08 sin 2g)*A_l*L = -0.096 A_l L u_rw v_rw
-  const double cw = P.cos_wind_dir * cpsi + P.sin_wind_dir * spsi;
-  const double sw = P.sin_wind_dir * cpsi - P.cos_wind_dir * spsi;
-  const double u_rw = P.wind_speed * cw - u;
-  const double v_rw = P.wind_speed * sw - v;
+  const double cw = H.cos_wind_dir * cpsi + H.sin_wind_dir * spsi;
+  const double sw = H.sin_wind_dir * cpsi - H.cos_wind_dir * spsi;
+  const double u_rw = H.wind_speed * cw - u;
+  const double v_rw = H.wind_speed * sw - v;
   const double vmag = SENV_SQRT(u_rw * u_rw + v_rw * v_rw);
-  const Derived& D = derived_of(P);
-  const double tau_u = D.wind_cu * vmag * u_rw;
-  const double tau_v = D.wind_cv * vmag * v_rw;
-  const double tau_n = D.wind_cn * u_rw * v_rw;
+  const double tau_u = H.wind_cu * vmag * u_rw;
+  const double tau_v = H.wind_cv * vmag * v_rw;
+  const double tau_n = H.wind_cn * u_rw * v_rw;
 #else
   double sw, cw;
   sincos(P.wind_dir - s.yaw, &sw, &cw);
-  const double u_rw = P.wind_speed * cw - u;
-  const double v_rw = P.wind_speed * sw - v;
+  const double u_rw = H.wind_speed * cw - u;
+  const double v_rw = H.wind_speed * sw - v;
   const double gamma_rw = -atan2(v_rw, u_rw);
   const double wind_rw2 = u_rw * u_rw + v_rw * v_rw;
   double sg, cg;
@@ -316,31 +324,31 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double tau_n = tau_coeff * c_n * P.proj_area_l * P.l_ship;
 #endif
   // --- kinetics (x_g = 0, diagonal mass matrix)
-  const double m = P.mass;
+  const double m = H.mass;
   const double crb0 = (-m * v) * r;
   const double crb1 = (m * u) * r;
   const double crb2 = (m * v) * u + (-m * u) * v;
-  const double ca0 = (P.y_dv * v_r) * r;
-  const double ca1 = (-P.x_du * u_r) * r;
-  const double ca2 = (-P.y_dv * v_r) * u_r + (P.x_du * u_r) * v_r;
-  const double dmp0 = (P.lin_damp_u + P.ku * u) * u_r;
-  const double dmp1 = (P.lin_damp_v + P.kv * v) * v_r;
-  const double dmp2 = (P.lin_damp_r + P.kr * r) * r;
+  const double ca0 = (H.y_dv * v_r) * r;
+  const double ca1 = (-H.x_du * u_r) * r;
+  const double ca2 = (-H.y_dv * v_r) * u_r + (H.x_du * u_r) * v_r;
+  const double dmp0 = (H.lin_damp_u + H.ku * u) * u_r;
+  const double dmp1 = (H.lin_damp_v + H.kv * v) * v_r;
+  const double dmp2 = (H.lin_damp_r + H.kr * r) * r;
   const double f0 = -crb0 - ca0 - dmp0 + tau_u + 0.0 + thrust;
   const double f1 = -crb1 - ca1 - dmp1 + tau_v + 0.0 + f_rudder_v;
   const double f2 = -crb2 - ca2 - dmp2 + tau_n + 0.0 + f_rudder_r;
-  const double d_u = P.inv_m_u * f0;
-  const double d_v = P.inv_m_v * f1;
-  const double d_r = P.inv_m_r * f2;
+  const double d_u = H.inv_m_u * f0;
+  const double d_v = H.inv_m_v * f1;
+  const double d_r = H.inv_m_r * f2;
   // --- forward Euler
-  const double dt = P.dt;
+  const double dt = H.dt;
   s.north = s.north + d_north * dt;
   s.east = s.east + d_east * dt;
   s.yaw = s.yaw + r * dt;
   s.u = s.u + d_u * dt;
   s.v = s.v + d_v * dt;
   s.r = s.r + d_r * dt;
-  if (MODEL != SHIPENV_MODEL_SIMPLE) s.omega = s.omega + d_omega * P.dt_shaft;
+  if (MODEL != SHIPENV_MODEL_SIMPLE) s.omega = s.omega + d_omega * H.dt_shaft;
   s.time = s.time + dt;
 }
 
@@ -698,7 +706,7 @@ __device__ SENV_SBMPC_ARGMIN_INLINE int sbmpc_warp_argmin(const SbmpcIn& mine, i
 }
 
 // shared-memory staging of the parameter block
-struct SharedBlock {
+struct alignas(16) SharedBlock {
   ShipEnvParams p;
   DerivedSlot drv[2];                    // see derived_of()
   double roa2, seg_len2;                 // roa * roa (check_condition.py:181-204), 2 * AB segment length
@@ -743,6 +751,62 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     const double margin = P.l_ship / 2;
     D.hz_min_n = sb.p.map_min_n + margin; D.hz_max_n = sb.p.map_max_n - margin;
     D.hz_min_e = sb.p.map_min_e + margin; D.hz_max_e = sb.p.map_max_e - margin;
+    // copies of the parameters the step reads, in its order
+    D.los_limit = P.los_limit;
+    D.los_ki = P.los_ki;
+    D.inv_ctrl_dt = P.inv_ctrl_dt;
+    D.ctrl_dt = P.ctrl_dt;
+    D.hdg_kp = P.hdg_kp;
+    D.hdg_kd = P.hdg_kd;
+    D.hdg_ki = P.hdg_ki;
+    D.max_rudder = P.max_rudder;
+    D.desired_speed = P.desired_speed;
+    D.spd_kp = P.spd_kp;
+    D.spd_kd = P.spd_kd;
+    D.spd_ki = P.spd_ki;
+    D.max_thrust = P.max_thrust;
+    D.dt = P.dt;
+    D.cur_n = P.cur_n;
+    D.cur_e = P.cur_e;
+    D.c_rudder_v = P.c_rudder_v;
+    D.c_rudder_r = P.c_rudder_r;
+    D.cos_wind_dir = P.cos_wind_dir;
+    D.sin_wind_dir = P.sin_wind_dir;
+    D.wind_speed = P.wind_speed;
+    D.mass = P.mass;
+    D.y_dv = P.y_dv;
+    D.x_du = P.x_du;
+    D.lin_damp_u = P.lin_damp_u;
+    D.ku = P.ku;
+    D.lin_damp_v = P.lin_damp_v;
+    D.kv = P.kv;
+    D.lin_damp_r = P.lin_damp_r;
+    D.kr = P.kr;
+    D.inv_m_u = P.inv_m_u;
+    D.inv_m_v = P.inv_m_v;
+    D.inv_m_r = P.inv_m_r;
+    D.l_ship = P.l_ship;
+    D.nav_fail_tol = P.nav_fail_tol;
+    D.sim_time = P.sim_time;
+    D.kp_ship_speed = P.kp_ship_speed;
+    D.ki_ship_speed = P.ki_ship_speed;
+    D.max_shaft_speed = P.max_shaft_speed;
+    D.kp_shaft_speed = P.kp_shaft_speed;
+    D.ki_shaft_speed = P.ki_shaft_speed;
+    D.p_me = P.p_me;
+    D.p_el = P.p_el;
+    D.tq_me_max = P.tq_me_max;
+    D.tq_el_max = P.tq_el_max;
+    D.d_me = P.d_me;
+    D.r_me = P.r_me;
+    D.d_hsg = P.d_hsg;
+    D.r_hsg = P.r_hsg;
+    D.k_torque = P.k_torque;
+    D.jp = P.jp;
+    D.thrust_coeff = P.thrust_coeff;
+    D.dt_shaft = P.dt_shaft;
+    D.k_thrust = P.k_thrust;
+    D.thrust_tau = P.thrust_tau;
     if (threadIdx.x == 0) { sb.roa2 = sb.p.roa * sb.p.roa; sb.seg_len2 = sb.p.ab_segment_length * 2; }
   }
   for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
@@ -1275,7 +1339,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
     }
     if (stepping) {
-      const double dt = P.dt;
+      const double dt = derived_of(P).dt;
       if (stop_branch) {
         // stopped ship: log row repeated, clock advanced twice (env.py:451-479)
         log_repeat_row(dv, 2 * env + role, tlog_n, s.time);
@@ -1319,7 +1383,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     int my_flags = 0;
     double ra = 0.0, rb = 0.0;
     if (running) {
-      const double len = P.l_ship;
+      const double len = derived_of(P).l_ship;
       const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
       // (four comparisons combined without short-circuit branches)
       const Derived& D = derived_of(P);
@@ -1329,11 +1393,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
       // sqrt(nextafter(40000)) rounds above 200)
       const bool reached = (dn * dn + de * de) <= 40000.0;
-      bool nav_fail = fabs(s.e_ct) > P.nav_fail_tol;
+      bool nav_fail = fabs(s.e_ct) > derived_of(P).nav_fail_tol;
       if (role == 1) nav_fail = (travel_dist > sb.seg_len2) || (travel_time > INFINITY) || nav_fail;
       my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
       // is_within_simu_time_limit on the test ship's clock (check_condition.py:206-213)
-      if (role == 0 && s.time > P.sim_time) my_flags |= 16;
+      if (role == 0 && s.time > derived_of(P).sim_time) my_flags |= 16;
       if (MODE == MODE_STEP && role == 1 && stage == 0) {
         // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
         const double rn = s.north - s.wn, re = s.east - s.we;
