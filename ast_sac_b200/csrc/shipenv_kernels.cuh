@@ -549,7 +549,8 @@ __device__ __forceinline__ double wrap_pmpi(double a) {     // wrap_angle_to_pmp
 #endif
 // cost of behaviour b (SBMPC.cost_func, sbmpc.py:190-296, for the prediction of linear_pred,
 // sbmpc_misc.py:102-122, against Obstacle.calculate_trajectory, sbmpc_misc.py:58-83)
-__device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b, double obs_l, double obs_w) {
+__device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b, double obs_l, double obs_w,
+                                                        const double* __restrict__ inv_t) {
   const int ic = b >> 2, jp = b & 3;
   const double chi_ca = (-30.0 + 10.0 * (double)ic) * (kPi / 180.0);       // np.deg2rad(Chi_ca_[ic])
   const double p_ca = (jp == 0) ? 0.4 : ((jp == 1) ? 0.6 : ((jp == 2) ? 0.8 : 1.0));
@@ -654,9 +655,33 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
         if (hi < (double)k_hi) k_hi = (hi > -1.0e6) ? (int)ceil(hi) : 0;
       }
     } else if (!(qc < 0.0)) k_hi = 0;                          // no relative motion and out of range
-    for (int k = k_lo; k <= k_hi; ++k) {
+    // The window's samples without branches, two at a time: almost every sample inside the window goes the whole
+    // way (root, sector, both divisions), and the loop was bound by the latency of that one dependent chain.  The
+    // sector logic collapses to one comparison -- ds_min <= the sector's safety distance <= ds_max, so the two
+    // shortcuts of sample() decide what `dist < ds_sector` decides -- and 1 / t comes from a table (exactly rounded).
+    auto sample_window = [&](int k) {
       const double kk = (double)k;
-      sample(e10 + kk * w0, e11 + kk * w1, (kk + 2.0) * kSbDt, otB, ccB);
+      const double e0 = e10 + kk * w0, e1 = e11 + kk * w1;
+      const double d2 = e0 * e0 + e1 * e1;
+      const double dist = SENV_SQRT(d2);
+      const bool in_range = ((int)(d2 < far2) & (int)(dist < d_close)) != 0;
+      const double xc = e1 * co - e0 * so, ys = -(e0 * co + e1 * so);
+      const bool behind = ((int)(ys > 0.0) & (int)(xc < 0.3665012267242973 * dist)) != 0;
+      const double ds_i = otB ? ds_ot : (behind ? ds_behind : ds_ahead);
+      const double q = SENV_DIV(d_safe, dist);
+      const double R = inv_t[k + 1] * ((q * q) * (q * q));
+      const double H0 = ccB * R + 0.0;
+      return (in_range && dist < ds_i) ? H0 : 0.0;
+    };
+    int k = k_lo;
+    for (; k + 1 <= k_hi; k += 2) {
+      const double Ha = sample_window(k), Hb = sample_window(k + 1);
+      if (Ha > H1) H1 = Ha;
+      if (Hb > H1) H1 = Hb;
+    }
+    if (k <= k_hi) {
+      const double Ha = sample_window(k);
+      if (Ha > H1) H1 = Ha;
     }
   }
 #else
@@ -683,7 +708,8 @@ __device__ SENV_SBMPC_INLINE double sbmpc_behaviour_cost(const SbmpcIn in, int b
 #ifndef SENV_SBMPC_ARGMIN_INLINE
 #define SENV_SBMPC_ARGMIN_INLINE __noinline__
 #endif
-__device__ SENV_SBMPC_ARGMIN_INLINE int sbmpc_warp_argmin(const SbmpcIn& mine, int src, int lane, double obs_l, double obs_w) {
+__device__ SENV_SBMPC_ARGMIN_INLINE int sbmpc_warp_argmin(const SbmpcIn& mine, int src, int lane, double obs_l, double obs_w,
+                                                         const double* __restrict__ inv_t) {
   SbmpcIn in;
   in.os_x = __shfl_sync(FULL_MASK, mine.os_x, src); in.os_y = __shfl_sync(FULL_MASK, mine.os_y, src);
   in.os_v = __shfl_sync(FULL_MASK, mine.os_v, src);
@@ -693,7 +719,7 @@ __device__ SENV_SBMPC_ARGMIN_INLINE int sbmpc_warp_argmin(const SbmpcIn& mine, i
   in.u_d = __shfl_sync(FULL_MASK, mine.u_d, src); in.chi_d = __shfl_sync(FULL_MASK, mine.chi_d, src);
   in.chi_last = __shfl_sync(FULL_MASK, mine.chi_last, src); in.p_last = __shfl_sync(FULL_MASK, mine.p_last, src);
   double cost = INFINITY;
-  if (lane < kSbBehaviours) cost = sbmpc_behaviour_cost(in, lane, obs_l, obs_w);
+  if (lane < kSbBehaviours) cost = sbmpc_behaviour_cost(in, lane, obs_l, obs_w, inv_t);
   if (!(cost < INFINITY)) cost = INFINITY;      // NaN / inf never win the reference's `cost_i < cost`
   int idx = lane;
 #pragma unroll
@@ -710,6 +736,7 @@ struct alignas(16) SharedBlock {
   ShipEnvParams p;
   DerivedSlot drv[2];                    // see derived_of()
   double roa2, seg_len2;                 // roa * roa (check_condition.py:181-204), 2 * AB segment length
+  double sb_inv_t[50];                   // SBMPC: 1 / t of prediction sample i, t = (i + 1) * DT_ (sbmpc.py:262)
   double bbox[SHIPENV_MAX_POLY * 4];
   double seg[2][SHIPENV_MAX_WP][3];      // per ship: bearing, sin, cos of the file route's segment wp[k-1] -> wp[k]
   unsigned char next[SHIPENV_MAX_VERT];
@@ -808,6 +835,10 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     D.k_thrust = P.k_thrust;
     D.thrust_tau = P.thrust_tau;
     if (threadIdx.x == 0) { sb.roa2 = sb.p.roa * sb.p.roa; sb.seg_len2 = sb.p.ab_segment_length * 2; }
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 50) {
+    const int i = (int)threadIdx.x - 64;
+    sb.sb_inv_t[i] = 1.0 / ((double)(i + 1) * 20.0);            // IEEE division: the value 1.0 / t has in the cost function
   }
   for (int i = threadIdx.x; i < 2 * SHIPENV_MAX_WP; i += blockDim.x) {
     const int r = i / SHIPENV_MAX_WP, k = i % SHIPENV_MAX_WP;
@@ -1321,7 +1352,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         while (todo) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
-          const int best = sbmpc_warp_argmin(in, src, lane, G.ship[1].l_ship, G.ship[1].w_ship);
+          const int best = sbmpc_warp_argmin(in, src, lane, G.ship[1].l_ship, G.ship[1].w_ship, sb.sb_inv_t);
           if (lane == src) {
             double u_best = 1.0, chi_best = 0.0;
             if (best >= 0) {
