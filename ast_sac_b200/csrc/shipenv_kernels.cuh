@@ -271,18 +271,19 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     // kinetics before it is integrated
     const double power = cmd * (H.p_me + H.p_el);
     thrust = s.omega;
-    d_omega = (-H.k_thrust * s.omega + power) / H.thrust_tau;
+    d_omega = SENV_DIV(-H.k_thrust * s.omega + power, H.thrust_tau);
   } else {
     const double w = s.omega;
-    // (the divisions stay exact in both builds: replacing them by reciprocal multiplications moved the
-    //  ill-conditioned detailed model past 1e-9 on one golden episode, rl_dt4_PTO)
-    const double a_me = cmd * H.p_me / (w + 0.1);
+    // (the divisions stay IEEE divisions in both builds -- replacing them by reciprocal multiplications moved the
+    //  ill-conditioned detailed model past 1e-9 on one golden episode, rl_dt4_PTO; the fast build takes them by
+    //  the library's fast-path sequence without its slow-path branch, same bits, shipenv_math.cuh)
+    const double a_me = SENV_DIV(cmd * H.p_me, w + 0.1);
     const double tq_me = (H.tq_me_max < a_me) ? H.tq_me_max : a_me;
-    const double a_el = cmd * H.p_el / (w + 0.1);
+    const double a_el = SENV_DIV(cmd * H.p_el, w + 0.1);
     const double tq_el = (H.tq_el_max < a_el) ? H.tq_el_max : a_el;
-    const double eq_me = (tq_me - H.d_me * w) / H.r_me;
-    const double eq_hsg = (tq_el - H.d_hsg * w) / H.r_hsg;
-    d_omega = (eq_me + eq_hsg - H.k_torque * (w * w)) / H.jp;
+    const double eq_me = SENV_DIV(tq_me - H.d_me * w, H.r_me);
+    const double eq_hsg = SENV_DIV(tq_el - H.d_hsg * w, H.r_hsg);
+    d_omega = SENV_DIV(eq_me + eq_hsg - H.k_torque * (w * w), H.jp);
     thrust = H.thrust_coeff * w * fabs(w);
   }
   // --- current in the body frame, rudder forces
@@ -447,7 +448,7 @@ __device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, 
       const double l2 = dx * dx + dy * dy;
       double t = 0.0;
       if (l2 != 0.0) {
-        t = ((px - ax) * dx + (py - ay) * dy) / l2;
+        t = SENV_DIV((px - ax) * dx + (py - ay) * dy, l2);
         t = (t < 1.0) ? t : 1.0;
         t = (t > 0.0) ? t : 0.0;
       }
@@ -456,7 +457,8 @@ __device__ __forceinline__ double map_distance(const MapView& mp, double n_pos, 
       best2 = (d2 < best2) ? d2 : best2;
     }
   }
-  return sqrt(best2);   // sqrt is monotonic and correctly rounded: sqrt(min d2) == min sqrt(d2)
+  // sqrt is monotonic and correctly rounded: sqrt(min d2) == min sqrt(d2); no listed segment: inf
+  return (best2 < INFINITY) ? SENV_SQRT(best2) : INFINITY;
 }
 
 // is_pos_inside_obstacles (check_condition.py:48-78): is any of the four corners of the L x L square
@@ -1442,8 +1444,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         // RewardDesign3/4 with per-role constants, one exp() call site for both roles
         const double g_scale = role == 0 ? 175000.0 : 50000.0;
         const double n_tol = role == 0 ? 3000.0 : 500.0, n_scale = role == 0 ? 1250000.0 : 12500.0;
-        if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : senv_exp(-(gd * gd) / g_scale);
-        rb = (aect < n_tol) ? senv_exp(-((aect - n_tol) * (aect - n_tol)) / n_scale) : 1.0;
+        if (gd <= 1000.0) ra = (gd < 0.0) ? 1.0 : senv_exp(SENV_DIV(-(gd * gd), g_scale));
+        rb = (aect < n_tol) ? senv_exp(SENV_DIV(-((aect - n_tol) * (aect - n_tol)), n_scale)) : 1.0;
         if (role == 1) { ra = -ra; rb = -rb; }
       }
     }
@@ -1478,9 +1480,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           beta = py_mod(beta + kPi, 2 * kPi) - kPi;
           const bool overtaking = !(fabs(beta) < 15.0 * (kPi / 180.0)) && (fabs(beta) > 165.0 * (kPi / 180.0));
           // head-on or crossing -> RewardDesign4(target 0, 2e8); the "overtake" branch is dead code
-          if (!overtaking) r1 = (distance < 0.0) ? 1.0 : senv_exp(-(distance * distance) / 200000000.0);
+          if (!overtaking) r1 = (distance < 0.0) ? 1.0 : senv_exp(SENV_DIV(-(distance * distance), 200000000.0));
         }
-        r_total = ((((r1 + ra) + rb) + p_ra) + p_rb) / 5;               // test terms, then obstacle terms
+        r_total = SENV_DIV((((r1 + ra) + rb) + p_ra) + p_rb, 5.0);               // test terms, then obstacle terms
       }
       bool st_done = false, st_terminal = false;
       out_info = 0;
