@@ -135,9 +135,9 @@ def measure_fp64_peak(device: int = 0, repeats: int = 5) -> float:
 
 
 def selftest_math(device: int = 0, n: int = 1 << 24, seed: int = 1):
-    """(sincos, atan, sqrt, division, exp, atan2) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA math
-    library: fast build, then strict build (12 numbers, all expected 0)."""
-    out = (C.c_ulonglong * 12)()
+    """(sincos, atan, sqrt, division, exp, atan2, fmod) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA
+    math library: fast build, then strict build (14 numbers, all expected 0)."""
+    out = (C.c_ulonglong * 14)()
     check(load().shipenv_selftest_math(device, n, seed, out))
     return list(out)
 

@@ -671,11 +671,11 @@ int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long lo
     return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
   CUDA_TRY(cudaSetDevice(device));
   unsigned long long* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, 12 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(dev, 0, 12 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&dev, 14 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(dev, 0, 14 * sizeof(unsigned long long)));
   CUDA_TRY(senv_fast::launch_math_selftest(n, seed, dev, nullptr));
-  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 6, nullptr));
-  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 12 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 7, nullptr));
+  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 14 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   cudaFree(dev);
   return SHIPENV_OK;
 }

@@ -511,7 +511,7 @@ __device__ __forceinline__ bool pos_inside_obstacles_slow(const double* ve, cons
 }
 
 __device__ __forceinline__ double py_mod(double a, double b) {   // Python / NumPy float modulo
-  double m = fmod(a, b);
+  double m = senv_fmod(a, b, 1.0 / b);                          // (b is a literal at both call sites: 1 / b folds)
   if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
   else m = copysign(0.0, b);
   return m;

@@ -67,11 +67,12 @@ def _golden_conditioning(meta, actions):
 
 
 def test_device_math_equals_cuda_math_library_bit_for_bit():
-    """csrc/shipenv_math.cuh: constant-bank sincos / atan / exp / atan2 (both builds) and the fast build's
-    branch-free sqrt / division return the CUDA math library's bits (2^24 + 2^22 pseudo-random arguments, two seeds)."""
+    """csrc/shipenv_math.cuh: constant-bank sincos / atan / exp / atan2, the loop-free fmod (both builds) and the
+    fast build's branch-free sqrt / division return the CUDA math library's bits (2^24 + 2^22 pseudo-random
+    arguments, two seeds)."""
     for n, seed in ((1 << 24, 1), (1 << 22, 12345)):
         counts = L.selftest_math(0, n, seed)
-        assert counts == [0] * 12, f"sincos/atan/sqrt/div/exp/atan2 mismatches (fast, strict) = {counts}"
+        assert counts == [0] * 14, f"sincos/atan/sqrt/div/exp/atan2/fmod mismatches (fast, strict) = {counts}"
 
 
 # ------------------------------------------------------------------------------------------------
