@@ -1475,10 +1475,20 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         const double distance = SENV_SQRT(d2);
         double r1 = 0.0;
         if (distance < 10000.0) {
+#if SENV_FAST_MATH
+          // encounter type (reward_function.py:82-112): beta = wrap(atan2(dy, dx) - psi) lies in [-pi, pi], and the
+          // only class that changes the reward is |beta| > 165 deg, i.e. cos(beta) < cos(165 deg) with
+          // cos(beta) = (dx cos psi + dy sin psi) / distance: one sincos of the heading instead of atan2 + a modulo.
+          // Same decision as the angle form up to the rounding of either (beta exactly at 165 deg has measure zero).
+          double s_yaw, c_yaw;
+          senv_sincos(s.yaw, &s_yaw, &c_yaw);
+          const bool overtaking = (dx * c_yaw + dy * s_yaw) < -0.9659258262890682 * distance;   // cos(165.0 * (pi / 180))
+#else
           const double phi = senv_atan2(dy, dx);
           double beta = phi - s.yaw;
           beta = py_mod(beta + kPi, 2 * kPi) - kPi;
           const bool overtaking = !(fabs(beta) < 15.0 * (kPi / 180.0)) && (fabs(beta) > 165.0 * (kPi / 180.0));
+#endif
           // head-on or crossing -> RewardDesign4(target 0, 2e8); the "overtake" branch is dead code
           if (!overtaking) r1 = (distance < 0.0) ? 1.0 : senv_exp(SENV_DIV(-(distance * distance), 200000000.0));
         }
