@@ -35,6 +35,11 @@
 #define SENV_REFILL_MIN 1   // lane pairs of a warp that must be free before they fetch (1 = fetch at once;
                             // batching 2/4/8 measured slower: 9.63 / 9.87 / 11.5 ms vs 9.35 ms per episode)
 #endif
+#ifdef SENV_NO_YAW_CARRY
+#define defined_SENV_NO_YAW_CARRY true
+#else
+#define defined_SENV_NO_YAW_CARRY false
+#endif
 #ifndef SENV_MIN_BLOCKS
 #define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
 #endif
@@ -182,7 +187,8 @@ struct NoStepHook { __device__ __forceinline__ void operator()(double, double) c
 template <int MODEL, class Hook = NoStepHook>
 __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
                                           bool collav_hit, double collav_bias, double heading_offset,
-                                          double speed_factor, double* log_row = nullptr, Hook hook = Hook()) {
+                                          double speed_factor, double* log_row = nullptr, Hook hook = Hook(),
+                                          double2* yaw_sc = nullptr) {
   const Derived& H = derived_of(P);   // the step's parameters in reading order (see Derived)
   // --- NavigationSystem.next_wpt
   {
@@ -257,7 +263,10 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   }
   // --- kinematics
   double spsi, cpsi;
-  senv_sincos(s.yaw, &spsi, &cpsi);
+  // yaw_sc (optional): sin / cos of the heading carried from the previous step -- the caller needs them for the
+  // heading the step ends with (the encounter type of the AST reward), and that heading is the next step's input
+  if (yaw_sc) { spsi = yaw_sc->x; cpsi = yaw_sc->y; }
+  else senv_sincos(s.yaw, &spsi, &cpsi);
   const double u = s.u, v = s.v, r = s.r;
   const double d_north = cpsi * u + (-spsi) * v;
   const double d_east = spsi * u + cpsi * v;
@@ -351,6 +360,7 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   s.r = s.r + d_r * dt;
   if (MODEL != SHIPENV_MODEL_SIMPLE) s.omega = s.omega + d_omega * H.dt_shaft;
   s.time = s.time + dt;
+  if (yaw_sc) senv_sincos(s.yaw, &yaw_sc->x, &yaw_sc->y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1213,6 +1223,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   double* const scratch_base = reinterpret_cast<double*>(__cvta_shared_to_generic(scratch_addr));
   struct { double& log_n; double& log_e; double& u_pre; } scratch{scratch_base[0], scratch_base[128], scratch_base[256]};
   double pending_dist = 0.0;
+  // rl_env, fast build: sin / cos of this ship's heading, carried from step to step (see ship_step's yaw_sc)
+  constexpr bool CARRY_YAW_SC = IS_RL && (SENV_FAST_MATH != 0) && !defined_SENV_NO_YAW_CARRY;
+  double2 yaw_sc = make_double2(0.0, 1.0);
   int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
   double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)
   int sampling_count = 0, flags = 0, n_iw = 0;
@@ -1305,6 +1318,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (lstate == LS_RUN) {
         load_segment_points(rt, n_iw, s);
         tlog_n = log_begin(dv, env, sidx);
+        if (CARRY_YAW_SC) senv_sincos(s.yaw, &yaw_sc.x, &yaw_sc.y);
       }
     }
 
@@ -1392,7 +1406,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         const double pre_n = s.north, pre_e = s.east;
         ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
                          log_next_row(dv, 2 * env + role, tlog_n),
-                         [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); });
+                         [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); },
+                         CARRY_YAW_SC ? &yaw_sc : nullptr);
         if (role == 1 && IS_IW) {
           if (flags & SHIPENV_FLAG_TRACKER) {
             // travel tracker on the two last logged rows (env.py:526-534)
@@ -1481,7 +1496,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           // cos(beta) = (dx cos psi + dy sin psi) / distance: one sincos of the heading instead of atan2 + a modulo.
           // Same decision as the angle form up to the rounding of either (beta exactly at 165 deg has measure zero).
           double s_yaw, c_yaw;
-          senv_sincos(s.yaw, &s_yaw, &c_yaw);
+          if (CARRY_YAW_SC) { s_yaw = yaw_sc.x; c_yaw = yaw_sc.y; }   // of the heading after this step (ship_step)
+          else senv_sincos(s.yaw, &s_yaw, &c_yaw);
           const bool overtaking = (dx * c_yaw + dy * s_yaw) < -0.9659258262890682 * distance;   // cos(165.0 * (pi / 180))
 #else
           const double phi = senv_atan2(dy, dx);
