@@ -40,7 +40,7 @@ N_RL_STEPS = 9
 #    ncu capture under profiles/ (includes the CUDA math library's sin/cos/atan2/exp internals and
 #    the map-geometry tests); filled in from profiles/r01_ncu_summary.md.
 FLOP_ALGO = {"colav_iw": 370.0 + 26.0, "rl": 450.0 + 31.0}
-FLOP_EXEC = {"colav_iw": 561.0, "rl": 1060.0}     # profiles/r01_ncu_summary.md part 4, section 2 (fast build)
+FLOP_EXEC = {"colav_iw": 561.0, "rl": 976.0}     # profiles/r01_ncu_summary.md part 4, section 2 (fast build)
 # DRAM bytes (read + written) of one k_env<MODE_STEP> launch over 1e5 environments, from the ncu --set full
 # capture summarised in profiles/r01_ncu_summary.md part 2 (dram__bytes_read.sum + dram__bytes_write.sum)
 TRAFFIC_PER_LAUNCH_1E5 = {"colav_iw": 40.3e6, "rl": 40.7e6}
