@@ -405,7 +405,7 @@ __device__ __forceinline__ bool poly_contains(const MapView& mp, int p, double x
   for (int i = a; i < b; ++i) {
     const double xi = mp.ve[i], yi = mp.vn[i];
     if ((yi > y) != (yj > y)) {
-      if (x < (xj - xi) * (y - yi) / (yj - yi) + xi) inside = !inside;
+      if (x < SENV_DIV((xj - xi) * (y - yi), yj - yi) + xi) inside = !inside;   // (yj != yi: the edge crosses y)
     }
     xj = xi; yj = yi;
   }
@@ -506,11 +506,11 @@ __device__ __forceinline__ bool pos_inside_obstacles_slow(const double* ve, cons
     for (int i = a; i < b; ++i) {
       const double xi = mp.ve[i], yi = mp.vn[i];
       if ((yi > y0) != (yj > y0)) {
-        const double xc = (xj - xi) * (y0 - yi) / (yj - yi) + xi;
+        const double xc = SENV_DIV((xj - xi) * (y0 - yi), yj - yi) + xi;
         in ^= (x0 < xc ? 1u : 0u) | (x1 < xc ? 2u : 0u);
       }
       if ((yi > y1) != (yj > y1)) {
-        const double xc = (xj - xi) * (y1 - yi) / (yj - yi) + xi;
+        const double xc = SENV_DIV((xj - xi) * (y1 - yi), yj - yi) + xi;
         in ^= (x0 < xc ? 4u : 0u) | (x1 < xc ? 8u : 0u);
       }
       xj = xi; yj = yi;
