@@ -35,11 +35,6 @@
 #define SENV_REFILL_MIN 1   // lane pairs of a warp that must be free before they fetch (1 = fetch at once;
                             // batching 2/4/8 measured slower: 9.63 / 9.87 / 11.5 ms vs 9.35 ms per episode)
 #endif
-#ifdef SENV_NO_YAW_CARRY
-#define defined_SENV_NO_YAW_CARRY true
-#else
-#define defined_SENV_NO_YAW_CARRY false
-#endif
 #ifndef SENV_MIN_BLOCKS
 #define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
 #endif
@@ -1180,13 +1175,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   unsigned sb_addr = (unsigned)__cvta_generic_to_shared(&sb_static);
   unsigned p_addr = (unsigned)__cvta_generic_to_shared(&sb_static.p.ship[role_tid]);
   asm volatile("" : "+r"(sb_addr), "+r"(p_addr));
-#ifdef SENV_ROLE_FROM_TID
-  const int role = role_tid;
-#else
   // the role, where it is needed again, from those two registers (a subtraction and a compare) rather than from
   // S2R SR_TID.X, whose latency sat in front of every role-dependent select
   const int role = (p_addr - sb_addr) != (unsigned)offsetof(SharedBlock, p.ship[0]) ? 1 : 0;
-#endif
   SharedBlock& sb = *reinterpret_cast<SharedBlock*>(__cvta_shared_to_generic(sb_addr));
   const ShipEnvParams& G = sb.p;
   const ShipEnvShipParams& P = *reinterpret_cast<const ShipEnvShipParams*>(__cvta_shared_to_generic(p_addr));
@@ -1224,7 +1215,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   struct { double& log_n; double& log_e; double& u_pre; } scratch{scratch_base[0], scratch_base[128], scratch_base[256]};
   double pending_dist = 0.0;
   // rl_env, fast build: sin / cos of this ship's heading, carried from step to step (see ship_step's yaw_sc)
-  constexpr bool CARRY_YAW_SC = IS_RL && (SENV_FAST_MATH != 0) && !defined_SENV_NO_YAW_CARRY;
+  constexpr bool CARRY_YAW_SC = IS_RL && (SENV_FAST_MATH != 0);
   double2 yaw_sc = make_double2(0.0, 1.0);
   int tlog_n = -1;             // rows in this ship's trajectory log (-1: not logged)
   double sb_p_last = 1.0, sb_chi_last = 0.0;   // SBMPCParams.P_ca_last_ / Chi_ca_last_ (both lanes of the pair)
@@ -1515,12 +1506,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       // One test for the common simulator step of a step(action) call: main loop (stage 0), no event bit of either
       // ship, radius of acceptance not reached, no collision and (run_colav, whose `done` needs both stop flags) no
       // stop flag set.  Nothing below changes anything then except the reward accumulators.
-#ifdef SENV_NO_PLAIN_STEP
-      const bool plain_step = false;
-#else
       const bool plain_step = (MODE == MODE_STEP) && (stage == 0) && (((t_flags | o_flags) & 63) == 0) &&
                               !is_collision && (IS_RL || ((s.stop | p_stop) == 0));
-#endif
       if (plain_step) {
         if (IS_RL) { acc_reward += r_total; out_reward = r_total; }
       } else {
