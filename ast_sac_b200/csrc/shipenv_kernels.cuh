@@ -755,17 +755,12 @@ __device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P)
   return *reinterpret_cast<const Derived*>(reinterpret_cast<const char*>(&P) + kOffset);
 }
 
-// with_routes = false copies the parameter block only and leaves out the bounding boxes, the per-ship derived
-// constants and the segment-bearing tables (64 atan2 + sincos per CTA): the step() prologue, one short CTA per 128
-// environments, reads none of them
-template <bool with_routes = true>
 __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
   unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sb.p);
   constexpr int words = sizeof(ShipEnvParams) / 8;
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   __syncthreads();
-  if (!with_routes) return;
   for (int p = threadIdx.x; p < sb.p.n_poly; p += blockDim.x) {
     double mne = INFINITY, mxe = -INFINITY, mnn = INFINITY, mxn = -INFINITY;
 #pragma unroll 1
@@ -1061,9 +1056,9 @@ __global__ void __launch_bounds__(128)
 k_prologue(DevView dv, const double* __restrict__ actions, unsigned long long* __restrict__ queue) {
   // the work-queue counters of the k_env launch that follows on the same stream restart at 0
   if (blockIdx.x == 0 && threadIdx.x < 2) queue[threadIdx.x] = 0ull;
-  __shared__ SharedBlock sb;
-  stage_params<false>(sb, dv.params);
-  const ShipEnvParams& G = sb.p;
+  // The parameter block is read where it lies (a dozen scalars per thread, the same addresses for every thread:
+  // L1 / L2 hits): staging 7 KB into shared memory per 128 environments cost more than the prologue's own work.
+  const ShipEnvParams& G = *dv.params;
   const long long B = dv.num_envs;
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= B) return;
