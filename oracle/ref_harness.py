@@ -267,8 +267,10 @@ MACHINERY_MODES = {
 }
 
 
-def build_rl_assets(args: Args, mode="PTI", test_init=None, obs_init=None, sim_time=10000):
-    """run/env_setup.py:32-239 -- the ShipModelAST pair (detailed machinery)."""
+def build_rl_assets(args: Args, mode="PTI", test_init=None, obs_init=None, sim_time=10000, omega_init=None):
+    """run/env_setup.py:32-239 -- the ShipModelAST pair (detailed machinery).  ``omega_init`` = (test, obs) initial
+    propeller shaft speeds [rad/s] when they differ from the script's 420 / 200 rpm (the one-ulp twins of
+    tests/golden/make_reference_twins.py)."""
     install_stubs()
     from rl_env.ship_in_transit.env import ShipAssets
     from rl_env.ship_in_transit.sub_systems.ship_model import (
@@ -311,12 +313,12 @@ def build_rl_assets(args: Args, mode="PTI", test_init=None, obs_init=None, sim_t
                              environment_config=env_config,
                              simulation_config=SimulationConfiguration(
                                  integration_step=args.time_step, simulation_time=sim_time, **ti),
-                             initial_propeller_shaft_speed_rad_per_s=420 * np.pi / 30)
+                             initial_propeller_shaft_speed_rad_per_s=(omega_init[0] if omega_init else 420 * np.pi / 30))
     obs_ship = ShipModelAST(ship_config=ship_config, machinery_config=machinery_config,
                             environment_config=env_config,
                             simulation_config=SimulationConfiguration(
                                 integration_step=args.time_step, simulation_time=sim_time, **oi),
-                            initial_propeller_shaft_speed_rad_per_s=200 * np.pi / 30)
+                            initial_propeller_shaft_speed_rad_per_s=(omega_init[1] if omega_init else 200 * np.pi / 30))
     map_obj = PolygonObstacle(MAP_DATA)
     gains = dict(kp_ship_speed=205.25, ki_ship_speed=0.0525, kp_shaft_speed=50, ki_shaft_speed=0.00025)
 

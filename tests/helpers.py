@@ -17,9 +17,6 @@ STATE_SCALE = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1e-3, 1.0, 1.0])
 # columns of ctrl_vec: e_ct_int, hdg_err_i, hdg_prev_err, spd_err_i, spd_prev_err, shaft_err_i, time
 CTRL_SCALE = np.array([1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0])
 REL_TOL = 1e-9          # BASELINE.json north_star tolerance (per state, over 10k steps)
-# PI integrators of the detailed model's throttle controller: the cascade has gain ~1e4 in a 1e-4 m/s band
-# (DESIGN.md section 2), its integrators are the first quantities to show the amplified 1-ulp differences
-CTRL_TOL_DETAILED = 1e-8
 
 
 def golden(name: str):
@@ -54,3 +51,57 @@ def oracle_ctrl_vec(s, detailed: bool) -> np.ndarray:
     else:
         sp = [s.spd_err_i, s.spd_prev_err, 0.0]
     return np.array([s.e_ct_int, s.hdg_err_i, s.hdg_prev_err] + sp + [s.time])
+
+
+# ------------------------------------------------------------------------------------------------
+# reference envelopes (tests/golden/make_reference_twins.py): how far the UNMODIFIED reference's own trajectory
+# moves when one initial state changes by one ulp.  A detailed-model state may differ from the reference by
+# REL_TOL, or -- only where the reference's own one-ulp twins drift further than REL_TOL / 10 -- by
+# ENVELOPE_K x that drift, capped at ENVELOPE_CAP; where ONE ulp moves the reference itself by more than the cap
+# (3 of 64 SBMPC episodes: up to 4e-4) the bound is that drift itself, factor 1.  Flags are waived only where a
+# reference twin flips them.
+# ------------------------------------------------------------------------------------------------
+ENVELOPE_K = 10.0
+ENVELOPE_CAP = 1e-6
+
+
+def envelope_tol(envelope: float, base: float = REL_TOL) -> float:
+    """Tolerance of a comparison whose reference one-ulp envelope is `envelope`."""
+    s = base / REL_TOL
+    return max(base, min(ENVELOPE_CAP * s, ENVELOPE_K * float(envelope) * s), float(envelope) * s)
+
+
+def golden_envelope(name: str):
+    """Per step(action) call of an rl_* golden: dict of envelope arrays (state, ctrl, reward, obs, travel,
+    flags_equal), or None when the golden has none (simple-model goldens need no allowance)."""
+    path = os.path.join(GOLDEN_DIR, "envelope_rl_goldens.npz")
+    z = np.load(path)
+    if f"{name}|state" not in z:
+        return None
+    return {k: z[f"{name}|{k}"] for k in ("state", "ctrl", "reward", "obs", "travel", "flags_equal")}
+
+
+REFERENCE_BATCHES = ["batch_rl_none_256", "batch_rl_sbmpc_64", "batch_rl_simple_64"]
+
+
+def compare_with_reference_batch(g, b, j, got_states, got_flags, got_reward, got_obs, stats):
+    """One environment after one step(action) call against the reference batch fixture `g`.
+    got_flags = (done, events, terminal, test_stop, obs_stop, n_substeps_total + 1, k_test, k_obs).
+    Returns False when the environment has to be dropped from further comparison (a waived flag)."""
+    env = float(g["env_state"][b, j])
+    tol = envelope_tol(env)
+    ref_flags = g["flags"][b, j]
+    if not np.array_equal(np.asarray(got_flags, dtype=np.int64), ref_flags.astype(np.int64)):
+        # only a flag that a one-ulp twin of the reference itself flips may differ
+        assert not g["flags_equal"][b, j], ("flag mismatch", b, j, list(got_flags), ref_flags.tolist())
+        stats["waived_flags"].append((b, j))
+        return False
+    err = float(rel_err(got_states, g["states"][b, j], STATE_SCALE).max())
+    assert err < tol, (b, j, err, env, tol)
+    if err >= REL_TOL:
+        stats["waived_states"].append((b, j, err, env))
+    stats["worst_tight"] = max(stats["worst_tight"], err if tol == REL_TOL else 0.0)
+    loose = tol / REL_TOL
+    assert rel_err(got_reward, g["reward"][b, j], 1e-3) < max(1e-8 * loose, 10 * float(g["env_reward"][b, j])), (b, j)
+    np.testing.assert_allclose(got_obs, g["obs"][b, j], rtol=2e-7 * loose, atol=1e-6 * loose + 10 * float(g["env_obs"][b, j]))
+    return True

@@ -19,8 +19,8 @@ from ast_sac_b200 import _lib as L
 from ast_sac_b200 import scenarios as S
 from oracle import oracle as O
 
-from helpers import (CTRL_SCALE, CTRL_TOL_DETAILED, REL_TOL, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
-                     rel_err, struct_from_bytes)
+from helpers import (CTRL_SCALE, REFERENCE_BATCHES, REL_TOL, STATE_SCALE, compare_with_reference_batch, envelope_tol, golden,
+                     golden_envelope, golden_names, oracle_ctrl_vec, oracle_ship_vec, rel_err, struct_from_bytes)
 from product_helpers import assets_from_meta, env_from_meta, product_ctrl_vec, product_ship_vec, product_states_all
 
 pytestmark = pytest.mark.gpu
@@ -30,40 +30,6 @@ MATH_MODES = ["strict", "fast"]     # both builds of the device code are held to
 
 def _sync():
     torch.cuda.synchronize()
-
-
-def _golden_conditioning(meta, actions):
-    """Per step() call, the largest relative state change of the ORACLE's own trajectory of this golden
-    episode when one initial state moves by one ulp (surge speed up/down, heading, shaft speed): how far
-    two IEEE-correct evaluations of the reference's formulas can legitimately drift apart (DESIGN.md
-    section 2; the detailed model's throttle cascade has gain ~1e4)."""
-    assets, m, args = assets_from_meta(meta)
-    base = O.env_config_from_assets(assets, m, args, O.ENV_RL if meta["kind"] == "rl" else O.ENV_COLAV_IW)
-    runs = []
-    for variant in range(5):
-        cfg = O.EnvConfig()
-        C.memmove(C.byref(cfg), C.byref(base), C.sizeof(O.EnvConfig))
-        for role in range(2):
-            c = cfg.ship[role]
-            if variant == 1:
-                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 10.0)
-            elif variant == 2:
-                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 0.0)
-            elif variant == 3:
-                c.initial_yaw_angle_rad = np.nextafter(c.initial_yaw_angle_rad, 10.0)
-            elif variant == 4:
-                c.initial_propeller_shaft_speed_rad_per_s = np.nextafter(c.initial_propeller_shaft_speed_rad_per_s, 0.0)
-        oe = O.OracleEnv(cfg)
-        oe.reset()
-        out = []
-        for a in actions:
-            r = oe.step(float(a))
-            out.append(np.stack([oracle_ship_vec(oe.st.ship[0]), oracle_ship_vec(oe.st.ship[1])]))
-            if r.done:
-                break
-        runs.append(out)
-    n = min(len(r) for r in runs)
-    return [max(float(rel_err(runs[0][j], runs[v][j], STATE_SCALE).max()) for v in range(1, 5)) for j in range(n)]
 
 
 def test_device_math_equals_cuda_math_library_bit_for_bit():
@@ -89,7 +55,11 @@ def test_iw_episode_matches_reference_golden(name, math_mode):
     obs0 = env.reset()
     assert np.array_equal(np.asarray(obs0), g["obs0"])
     n = int(g["n_valid"])
-    cond = None      # oracle 1-ulp conditioning of this episode, computed only if a detailed-model state exceeds REL_TOL
+    # Detailed model: the bar is 1e-9, widened only where the UNMODIFIED reference's own one-ulp twins of this
+    # episode drift apart (tests/golden/envelope_rl_goldens.npz, made by make_reference_twins.py); flags are
+    # bit-exact without exception (no reference twin flips one in any golden).
+    ref_env = golden_envelope(name) if detailed else None
+    widened = []
     for j in range(n):
         res = env.step(np.array([g["actions"][j]]))
         if is_rl:
@@ -105,26 +75,23 @@ def test_iw_episode_matches_reference_golden(name, math_mode):
         assert info["obs_ship_stop"] == bool(g["obs_stop"][j])
         k = env.next_wpt[0].cpu().numpy()
         assert k[0] == g["k_test"][j] and k[1] == g["k_obs"][j], (name, j, k)
-        loose = 1.0      # widening of the scalar checks of this step when the conditioning allowance applies
+        tol = envelope_tol(ref_env["state"][j]) if ref_env else REL_TOL
+        ctrl_tol = envelope_tol(max(ref_env["state"][j], ref_env["ctrl"][j])) if ref_env else REL_TOL
+        loose = tol / REL_TOL
         for role, key in ((0, "test"), (1, "obs")):
             e = rel_err(product_ship_vec(env, role), g[key + "_state"][j], STATE_SCALE)
-            tol, ctrl_tol = REL_TOL, (CTRL_TOL_DETAILED if detailed else REL_TOL)
-            if detailed and e.max() >= REL_TOL:
-                # the detailed model's conditioning: accept what one ulp of an initial state does to the
-                # oracle's own trajectory at this step (x10), never more than 1e-6; flags stay bit-exact
-                cond = cond or _golden_conditioning(meta, g["actions"][:n])
-                tol = min(1e-6, 10 * cond[j])
-                ctrl_tol = max(ctrl_tol, 10 * tol)
-                loose = max(loose, tol / REL_TOL)
-                print(f"[{name}/{math_mode}] step {j} {key}: err {e.max():.2e}, oracle 1-ulp conditioning {cond[j]:.2e}")
-            assert e.max() < tol, (name, j, key, e, cond)
+            assert e.max() < tol, (name, j, key, e, tol)
+            if e.max() >= REL_TOL:
+                widened.append((j, key, float(e.max()), float(ref_env["state"][j])))
             e = rel_err(product_ctrl_vec(env, role), g[key + "_ctrl"][j], CTRL_SCALE)
-            # controller integrators of the ill-conditioned detailed model: 1e-8
-            assert e.max() < ctrl_tol, (name, j, key, "ctrl", e)
-        assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < REL_TOL * loose
+            assert e.max() < ctrl_tol, (name, j, key, "ctrl", e, ctrl_tol)
+        assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < tol
         np.testing.assert_allclose(o, g["obs"][j], rtol=2e-7 * loose, atol=1e-6 * loose)
         if is_rl:
             assert rel_err(r, g["reward"][j], 1e-3) < 1e-8 * loose, (name, j, r, g["reward"][j])
+    if widened:
+        print(f"[{name}/{math_mode}] calls beyond 1e-9 but inside the reference's one-ulp envelope (call, ship, err, "
+              f"reference envelope): {widened}")
     # number of simulator steps: the reference log has one row per _step() plus the init_step row
     # (a sampling failure adds none)
     assert env.total_substeps() == int(g["n_log"][n - 1]) - 1
@@ -234,67 +201,84 @@ def _oracle_cfg(assets, env, kind):
     return O.env_config_from_assets(assets, env.map, env.args, kind)
 
 
-def _oracle_sensitivity(base_cfg, init_np, b, actions_row, upto_step):
-    """Largest relative state difference between two oracle runs of env b whose initial surge speeds
-    differ by one ulp, after step() calls 0..upto_step: the conditioning of the reference dynamics."""
-    finals = []
-    for variant in range(5):      # 0 = unperturbed; 1..4 = one-ulp changes of different initial states
-        cfg = O.EnvConfig()
-        C.memmove(C.byref(cfg), C.byref(base_cfg), C.sizeof(O.EnvConfig))
-        for role in range(2):
-            cfg.ship[role].initial_north_position_m = init_np[0, b, role]
-            cfg.ship[role].initial_east_position_m = init_np[1, b, role]
-            c = cfg.ship[role]
-            if variant == 1:
-                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 10.0)
-            elif variant == 2:
-                c.initial_forward_speed_m_per_s = np.nextafter(c.initial_forward_speed_m_per_s, 0.0)
-            elif variant == 3:
-                c.initial_yaw_angle_rad = np.nextafter(c.initial_yaw_angle_rad, 10.0)
-            elif variant == 4:
-                c.initial_propeller_shaft_speed_rad_per_s = np.nextafter(c.initial_propeller_shaft_speed_rad_per_s, 0.0)
-        oe = O.OracleEnv(cfg)
-        oe.reset()
-        for j in range(upto_step + 1):
-            r = oe.step(float(actions_row[j]))
-            if r.done:
-                break
-        finals.append(np.stack([oracle_ship_vec(oe.st.ship[0]), oracle_ship_vec(oe.st.ship[1])]))
-    return max(float(rel_err(finals[0], f, STATE_SCALE).max()) for f in finals[1:])
+@pytest.mark.parametrize("math_mode", MATH_MODES)
+@pytest.mark.parametrize("fixture", REFERENCE_BATCHES)
+def test_batched_rl_episodes_match_reference(fixture, math_mode):
+    """Detailed model (config 3's env): 256 (collav none) / 64 (sbmpc, simple) jittered MultiShipRLEnv episodes,
+    each compared with the UNMODIFIED REFERENCE's own run of the same seeded inputs (tests/golden/batch_rl_*.npz,
+    made by tests/golden/make_reference_twins.py).
+
+    Flags, event bits, step counts and waypoint indices are bit-exact; a flag may only differ where a one-ulp twin of
+    the reference itself flips it (none does in these batches, so zero are waived).  States meet 1e-9, widened to
+    min(1e-6, 10 x envelope) only where the reference's own one-ulp twins of that episode drift apart by the
+    envelope recorded in the fixture (the cascaded throttle controller with measured_shaft_speed = forward_speed has
+    gain ~1e4, rl_env controllers.py:185-189, env.py:397-401); the widened count is printed and bounded by the
+    number of (environment, call) points whose reference envelope exceeds 1e-10."""
+    g = golden(fixture)
+    meta = json.loads(str(g["meta"]))
+    B = meta["B"]
+    args = S.get_env_args(time_step=4, collav_mode=meta["collav"])
+    assets, _ = S.build_rl_assets(args)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=meta["pos_jitter_m"], seed=meta["seed_init"])
+    assert np.array_equal(init.cpu().numpy().reshape(7, B, 2), g["init"])        # same seeded inputs as the fixture
+    env, assets = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init, math_mode=math_mode)
+    actions = torch.from_numpy(g["actions"])
+    env.reset()
+    alive = np.ones(B, dtype=bool)
+    n_log = np.ones(B, dtype=np.int64)                      # rows of the reference's log: init_step + one per _step()
+    stats = dict(waived_flags=[], waived_states=[], worst_tight=0.0)
+    seen_events = 0
+    for j in range(9):
+        env.step(actions[:, j].cuda())
+        _sync()
+        info = env.info_buf.cpu().numpy()
+        nsub = env.nsub_buf.cpu().numpy()
+        obs = env.obs_buf.cpu().numpy()
+        rew = env.reward_buf.cpu().numpy()
+        states = product_states_all(env)
+        kk = env.next_wpt.cpu().numpy()
+        n_log += nsub
+        for b in range(B):
+            if not alive[b]:
+                continue
+            assert j < g["n_valid"][b]
+            flags = (bool(info[b] & L.INFO_DONE), int(info[b] & L.INFO_EVENT_MASK), bool(info[b] & L.INFO_TERMINAL),
+                     bool(info[b] & L.INFO_TEST_STOP), bool(info[b] & L.INFO_OBS_STOP), int(n_log[b]), int(kk[b, 0]),
+                     int(kk[b, 1]))
+            if not compare_with_reference_batch(g, b, j, states[b], flags, rew[b], obs[b], stats):
+                alive[b] = False
+                continue
+            seen_events |= flags[1]
+            if flags[0]:
+                alive[b] = False
+    assert not alive.any()
+    n_ill = int((g["env_state"] * 10 > REL_TOL).sum())
+    print(f"[{fixture}/{math_mode}] GPU vs reference: worst error of the calls held to 1e-9: {stats['worst_tight']:.2e}; "
+          f"calls inside the reference's one-ulp envelope only: {len(stats['waived_states'])} of {n_ill} eligible "
+          f"{[(b, j, f'{e:.1e}', f'{v:.1e}') for b, j, e, v in stats['waived_states']]}; waived flags: {stats['waived_flags']}")
+    assert not stats["waived_flags"]
+    assert len(stats["waived_states"]) <= n_ill
+    assert bin(seen_events).count("1") >= 4, bin(seen_events)
+    env.close()
 
 
 @pytest.mark.parametrize("math_mode", MATH_MODES)
-@pytest.mark.parametrize("kind,collav", [("rl", "none"), ("colav", "none"), ("rl", "simple"), ("colav", "simple"),
-                                         ("rl", "sbmpc"), ("colav", "sbmpc")])
-def test_batched_episodes_match_oracle(kind, collav, math_mode):
-    """256 environments, per-env random scoping angles and jittered start positions, full episodes
-    (9 step() calls); every environment is compared with its own scalar oracle run.
-
-    The detailed model's cascaded throttle controller (gain ~1e4 inside a 1e-4 m/s band, rl_env
-    controllers.py:185-189 with measured_shaft_speed = forward_speed) is ill-conditioned: a ONE-ulp
-    change of the initial surge speed moves the oracle's own trajectory by up to ~1e-8 within one
-    step() for a few percent of the environments.  An environment whose GPU-vs-oracle difference
-    exceeds REL_TOL is therefore only accepted if the oracle's own 1-ulp sensitivity at that point is
-    of the same order (and then dropped from further comparison); the simple model gets no such
-    allowance."""
+@pytest.mark.parametrize("collav", ["none", "simple", "sbmpc"])
+def test_batched_colav_episodes_match_oracle(collav, math_mode):
+    """Simple model (config 2's env): 256 environments, per-env random scoping angles and jittered start positions,
+    full episodes (9 step() calls); every environment is compared with its own scalar oracle run -- flags bit-exact,
+    states within 1e-9, no allowance of any kind."""
     B = 256
     args = S.get_env_args(time_step=4, collav_mode=collav)
-    if kind == "rl":
-        assets, m = S.build_rl_assets(args)
-    else:
-        assets, m = S.build_colav_assets(args, iw=True)
+    assets, m = S.build_colav_assets(args, iw=True)
     init = S.jittered_init_states(assets, B, pos_jitter_m=100.0, seed=1)
-    cls_kind = O.ENV_RL if kind == "rl" else O.ENV_COLAV_IW
-    if kind == "rl":
-        env, assets = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init, math_mode=math_mode)
-    else:
-        env, assets = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init, math_mode=math_mode)
+    env, assets = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init, math_mode=math_mode)
     gen = torch.Generator().manual_seed(0)
     actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
     actions[: B // 4] *= 0.1          # small angles keep the ships on a collision course
     env.reset()
     init_np = init.cpu().numpy().reshape(7, B, 2)
-    base_cfg = _oracle_cfg(assets, env, cls_kind)
+    base_cfg = _oracle_cfg(assets, env, O.ENV_COLAV_IW)
     oracles = []
     for b in range(B):
         cfg = O.EnvConfig()
@@ -305,8 +289,7 @@ def test_batched_episodes_match_oracle(kind, collav, math_mode):
         oe = O.OracleEnv(cfg)
         oe.reset()
         oracles.append(oe)
-    alive = np.ones(B, dtype=bool)        # still being compared
-    ill = []                              # (env, step, gpu error, oracle 1-ulp sensitivity)
+    alive = np.ones(B, dtype=bool)
     seen_events = 0
     worst = 0.0
     for j in range(9):
@@ -315,7 +298,6 @@ def test_batched_episodes_match_oracle(kind, collav, math_mode):
         info = env.info_buf.cpu().numpy()
         nsub = env.nsub_buf.cpu().numpy()
         obs = env.obs_buf.cpu().numpy()
-        rew = env.reward_buf.cpu().numpy()
         states = product_states_all(env)
         kk = env.next_wpt.cpu().numpy()
         for b in range(B):
@@ -325,30 +307,21 @@ def test_batched_episodes_match_oracle(kind, collav, math_mode):
             st = oracles[b].st
             assert r.error == 0
             err = max(rel_err(states[b, role], oracle_ship_vec(st.ship[role]), STATE_SCALE).max() for role in range(2))
-            flags_ok = (nsub[b] == r.n_substeps and (info[b] & L.INFO_EVENT_MASK) == r.events
-                        and bool(info[b] & L.INFO_DONE) == bool(r.done)
-                        and bool(info[b] & L.INFO_TERMINAL) == bool(r.terminal)
-                        and bool(info[b] & L.INFO_TEST_STOP) == bool(r.test_ship_stop)
-                        and bool(info[b] & L.INFO_OBS_STOP) == bool(r.obs_ship_stop)
-                        and kk[b, 0] == st.ship[0].next_wpt and kk[b, 1] == st.ship[1].next_wpt)
-            if err >= REL_TOL or not flags_ok:
-                sens = _oracle_sensitivity(base_cfg, init_np, b, actions[b].numpy(), j) if kind == "rl" else 0.0
-                assert kind == "rl" and sens > 1e-13 and err < max(1e-6, 10 * sens) and (flags_ok or sens > 1e-10), \
-                    (b, j, err, sens, flags_ok)
-                ill.append((b, j, err, sens))
-                alive[b] = False
-                continue
+            assert (nsub[b] == r.n_substeps and (info[b] & L.INFO_EVENT_MASK) == r.events
+                    and bool(info[b] & L.INFO_DONE) == bool(r.done)
+                    and bool(info[b] & L.INFO_TERMINAL) == bool(r.terminal)
+                    and bool(info[b] & L.INFO_TEST_STOP) == bool(r.test_ship_stop)
+                    and bool(info[b] & L.INFO_OBS_STOP) == bool(r.obs_ship_stop)
+                    and kk[b, 0] == st.ship[0].next_wpt and kk[b, 1] == st.ship[1].next_wpt), (b, j)
+            assert err < REL_TOL, (b, j, err)
             worst = max(worst, err)
             np.testing.assert_allclose(obs[b], np.array(r.obs[:]), rtol=2e-7, atol=1e-6)
-            if kind == "rl":
-                assert rel_err(rew[b], r.reward, 1e-3) < 1e-7, (b, j, rew[b], r.reward)
             seen_events |= r.events
             if r.done:
                 alive[b] = False
                 # finished environments are left alone by later calls
     assert not alive.any()
-    assert len(ill) <= B // 10, ill
-    print(f"[{kind}/{collav}/{math_mode}] worst rel err of well-conditioned envs {worst:.2e}; ill-conditioned envs: {ill}")
+    print(f"[colav/{collav}/{math_mode}] worst rel err {worst:.2e}")
     # the batch must have exercised several different endings
     assert bin(seen_events).count("1") >= 5, bin(seen_events)
     env.close()
@@ -506,6 +479,61 @@ def test_full_size_bare_rollout_1e6_ships_10k_steps_sample():
         e = rel_err(product_ship_vec(env, role, e=B - 1), out[-1], STATE_SCALE)
         assert e.max() < REL_TOL, (role, e)
         assert int(env.next_wpt[B - 1, role]) == wpt[-1]
+    env.close()
+
+
+def test_full_size_rl_episode_1e6_envs_jittered_with_reference_sample():
+    """BASELINE config 3 at size: 1e6 jittered MultiShipRLEnv (ShipModelAST, PTI) environments run a whole episode with
+    per-environment random scoping angles.  256 of them, scattered over the batch, are given the inputs of the
+    reference-run fixture batch_rl_none_256 and are compared with the unmodified reference's results (flags bit-exact,
+    states 1e-9 / reference envelope); the device step counter equals the sum of the per-call step counts; every
+    environment terminates; neighbours of the sampled environments (different inputs) did not leak into them."""
+    B = 1_000_000
+    g = golden("batch_rl_none_256")
+    nb = g["actions"].shape[0]
+    idx = np.arange(nb) * (B // nb) + 17                      # where the fixture's environments sit in the batch
+    args = S.get_env_args(time_step=4)
+    assets, _ = S.build_rl_assets(args)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=50.0, seed=5, device="cpu").reshape(7, B, 2)
+    init[:, idx, :] = torch.from_numpy(g["init"])
+    gen = torch.Generator().manual_seed(9)
+    actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
+    actions[idx] = torch.from_numpy(g["actions"])
+    env, assets = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init.reshape(7, 2 * B).cuda())
+    actions = actions.cuda()
+    env.reset()
+    idx_t = torch.from_numpy(idx).cuda()
+    alive = np.ones(nb, dtype=bool)
+    n_log = np.ones(nb, dtype=np.int64)
+    stats = dict(waived_flags=[], waived_states=[], worst_tight=0.0)
+    total = 0
+    for j in range(9):
+        env.step(actions[:, j])
+        total += int(env.nsub_buf.sum(dtype=torch.int64).item())
+        info = env.info_buf[idx_t].cpu().numpy()
+        nsub = env.nsub_buf[idx_t].cpu().numpy()
+        obs = env.obs_buf[idx_t].cpu().numpy()
+        rew = env.reward_buf[idx_t].cpu().numpy()
+        st = env.ship_f64.view(L.SF_COUNT, B, 2)[:, idx_t].cpu().numpy()
+        states = np.stack([st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[8]], axis=-1)      # [nb, 2, 8]
+        kk = env.next_wpt[idx_t].cpu().numpy()
+        n_log += nsub
+        for b in range(nb):
+            if not alive[b]:
+                continue
+            flags = (bool(info[b] & L.INFO_DONE), int(info[b] & L.INFO_EVENT_MASK), bool(info[b] & L.INFO_TERMINAL),
+                     bool(info[b] & L.INFO_TEST_STOP), bool(info[b] & L.INFO_OBS_STOP), int(n_log[b]), int(kk[b, 0]),
+                     int(kk[b, 1]))
+            ok = compare_with_reference_batch(g, b, j, states[b], flags, rew[b], obs[b], stats)
+            if not ok or flags[0]:
+                alive[b] = False
+    _sync()
+    assert not alive.any()
+    assert not stats["waived_flags"]
+    assert env.total_substeps() == total
+    assert bool(env.done_mask.all())
+    print(f"[1e6 rl] {total} simulator steps; sampled 256 vs reference: worst error held to 1e-9 {stats['worst_tight']:.2e}, "
+          f"inside the reference envelope only: {len(stats['waived_states'])}")
     env.close()
 
 

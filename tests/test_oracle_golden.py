@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from helpers import (CTRL_SCALE, CTRL_TOL_DETAILED, REL_TOL, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
+from helpers import (CTRL_SCALE, REFERENCE_BATCHES, REL_TOL, compare_with_reference_batch, STATE_SCALE, golden, golden_names, oracle_ctrl_vec, oracle_ship_vec,
                      rel_err, struct_from_bytes)
 
 
@@ -60,8 +60,12 @@ def _run_iw(name):
     assert np.array_equal(obs0, g["obs0"])
     n = int(g["n_valid"])
     detailed = cfg.ship[0].model_kind == O.MODEL_DETAILED
+    from helpers import envelope_tol, golden_envelope
+    ref_env = golden_envelope(name) if detailed else None      # the reference's own one-ulp drift per call
     n_sub = 0
     for j in range(n):
+        tol = envelope_tol(ref_env["state"][j]) if ref_env else REL_TOL
+        ctrl_tol = envelope_tol(max(ref_env["state"][j], ref_env["ctrl"][j])) if ref_env else REL_TOL
         r = env.step(float(g["actions"][j]))
         assert r.error == 0
         n_sub += r.n_substeps
@@ -77,15 +81,15 @@ def _run_iw(name):
         # FP64 states
         for who, key in ((0, "test"), (1, "obs")):
             e = rel_err(oracle_ship_vec(env.st.ship[who]), g[key + "_state"][j], STATE_SCALE)
-            assert e.max() < REL_TOL, (name, j, key, e)
+            assert e.max() < tol, (name, j, key, e)
             e = rel_err(oracle_ctrl_vec(env.st.ship[who], detailed), g[key + "_ctrl"][j], CTRL_SCALE)
-            # controller integrators of the ill-conditioned detailed model: 1e-8
-            assert e.max() < (CTRL_TOL_DETAILED if detailed else REL_TOL), (name, j, key, "ctrl", e)
-        assert rel_err(env.st.travel_dist, g["travel_dist"][j], 1.0) < REL_TOL
+            # 1e-9, widened only where the reference's own one-ulp twins drift (tests/golden/make_reference_twins.py)
+            assert e.max() < ctrl_tol, (name, j, key, "ctrl", e, ctrl_tol)
+        assert rel_err(env.st.travel_dist, g["travel_dist"][j], 1.0) < tol
         # float32 observation: allow 1 ulp of float32 where the FP64 value sits on a rounding boundary
         np.testing.assert_allclose(np.array(r.obs[:]), g["obs"][j], rtol=2e-7, atol=1e-6)
         if cfg.env_kind == O.ENV_RL:
-            assert rel_err(r.reward, g["reward"][j], 1e-3) < 1e-8, (name, j, r.reward, g["reward"][j])
+            assert rel_err(r.reward, g["reward"][j], 1e-3) < 1e-8 * (tol / REL_TOL), (name, j, r.reward, g["reward"][j])
     route_n = np.array(env.st.ship[1].wp_north[: env.st.ship[1].n_wp])
     route_e = np.array(env.st.ship[1].wp_east[: env.st.ship[1].n_wp])
     assert rel_err(route_n, g["obs_route_north"], 1.0).max() < 1e-12
@@ -167,3 +171,42 @@ def test_oracle_follows_reference_sampler_episode(name):
         assert r.events == g["events"][j]
         o = np.array(r.obs[:], dtype=np.float32)
     assert bool(g["dones"][n - 1, 0]) or n == meta["max_path_length"]
+
+
+# ------------------------------------------------------------------------------------------------
+# seeded batches run by the unmodified reference (tests/golden/make_reference_twins.py): the oracle against
+# the reference on 256 (collav none) / 64 (sbmpc) jittered MultiShipRLEnv episodes, tolerance tied to the
+# reference's own one-ulp envelope
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fixture", REFERENCE_BATCHES)
+def test_oracle_matches_reference_batch(fixture):
+    import json
+    from ast_sac_b200 import scenarios as S
+    g = golden(fixture)
+    meta = json.loads(str(g["meta"]))
+    B = meta["B"]
+    args = S.get_env_args(time_step=4, collav_mode=meta["collav"])
+    assets, m = S.build_rl_assets(args)
+    base = O.env_config_from_assets(assets, m, args, O.ENV_RL)
+    stats = dict(waived_flags=[], waived_states=[], worst_tight=0.0)
+    for b in range(B):
+        cfg = O.EnvConfig()
+        ctypes.memmove(ctypes.byref(cfg), ctypes.byref(base), ctypes.sizeof(O.EnvConfig))
+        for role in range(2):
+            cfg.ship[role].initial_north_position_m = g["init"][0, b, role]
+            cfg.ship[role].initial_east_position_m = g["init"][1, b, role]
+        oe = O.OracleEnv(cfg)
+        oe.reset()
+        n_log = 1
+        for j in range(int(g["n_valid"][b])):
+            r = oe.step(float(g["actions"][b, j]))
+            n_log += r.n_substeps
+            flags = (r.done, r.events, r.terminal, r.test_ship_stop, r.obs_ship_stop, oe.st.ship[1].n_log,
+                     oe.st.ship[0].next_wpt, oe.st.ship[1].next_wpt)
+            st = np.stack([oracle_ship_vec(oe.st.ship[0]), oracle_ship_vec(oe.st.ship[1])])
+            if not compare_with_reference_batch(g, b, j, st, flags, r.reward, np.array(r.obs[:]), stats):
+                break
+    print(f"[{fixture}] oracle vs reference: worst error of envs held to 1e-9: {stats['worst_tight']:.2e}; "
+          f"states inside the reference envelope only: {len(stats['waived_states'])}; waived flags: {stats['waived_flags']}")
+    assert not stats["waived_flags"]            # no reference twin flips a flag in these batches
+    assert len(stats["waived_states"]) <= (g["env_state"] * 10 > REL_TOL).sum()
