@@ -79,7 +79,8 @@ EXPORTS = [
     "shipenv_construct", "shipenv_reset", "shipenv_init_step", "shipenv_step", "shipenv_substeps",
     "shipenv_ship_rollout", "shipenv_reset_host", "shipenv_step_host", "shipenv_substeps_host",
     "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math", "shipenv_set_trajectory_log",
-    "shipenv_time_env_kernel", "shipenv_env_kernel_ms",
+    "shipenv_time_env_kernel", "shipenv_env_kernel_ms", "shipenv_map_query",
+    "shipenv_register_host", "shipenv_unregister_host",
 ]
 
 _lib = None
@@ -119,6 +120,9 @@ def load():
     L.shipenv_env_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
     L.shipenv_measure_fp64_peak.argtypes = [i32, i32, C.POINTER(C.c_double)]
     L.shipenv_selftest_math.argtypes = [i32, i64, C.c_uint64, vp]
+    L.shipenv_register_host.argtypes = [vp, vp, C.c_size_t]
+    L.shipenv_unregister_host.argtypes = [vp, vp]
+    L.shipenv_map_query.argtypes = [vp, i64, vp, vp, C.c_double, vp, vp, vp, vp]
     if L.shipenv_abi_version() != ABI_VERSION:
         raise ImportError("libshipenv.so ABI version mismatch; rebuild the extension")
     if L.shipenv_sizeof_params() != C.sizeof(Params):

@@ -14,6 +14,10 @@
 #include "shipenv.h"
 #include "shipenv_launch.h"
 
+#ifndef SHIPENV_STREAMING_K
+#define SHIPENV_STREAMING_K 8
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -39,6 +43,7 @@ struct shipenv {
   long long num_envs = 0;
   ShipEnvParams params;
   ShipEnvParams* params_dev = nullptr;
+  void* staged_dev = nullptr;         // the kernels' shared-memory block, rebuilt at every parameter upload
   ShipEnvBuffers buf{};
   bool bound = false;
   bool owns = false;
@@ -66,9 +71,11 @@ struct shipenv {
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
   cudaStream_t stream = nullptr;
+  cudaEvent_t ev_caller = nullptr;    // recorded on the caller's stream by every device-pointer entry point
+  bool caller_pending = false;
   // caller buffers of the *_host entry points that were page-locked with cudaHostRegister: the copies then
   // go straight between the caller's memory and the device (no staging memcpy)
-  struct HostReg { const void* ptr; size_t bytes; bool ok; };
+  struct HostReg { const void* ptr; size_t bytes; bool owned; };   // owned: registered by us (unregister at release)
   std::vector<HostReg> host_regs;
 };
 
@@ -110,7 +117,7 @@ int validate(const ShipEnvParams* p, long long num_envs) {
 }
 
 SenvView view(const shipenv* h) {
-  return SenvView{h->params_dev, h->buf, h->num_envs, h->grid, h->params.collav == SHIPENV_COLLAV_SBMPC ? 1 : 0,
+  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav,
                   h->log_dev, h->log_count_dev, h->log_envs, h->log_capacity};
 }
 
@@ -122,13 +129,24 @@ int check_ready(const shipenv* h, bool need_constructed) {
   return SHIPENV_OK;
 }
 
+// The *_host entry points run on the handle's own stream.  Work submitted through the device-pointer entry points
+// on a caller stream is tracked with an event so that a later *_host call is ordered after it (a C caller may mix the
+// two families without a synchronisation of its own).
+int note_caller_stream(shipenv* h, cudaStream_t st) {
+  if (h->stream && st == h->stream) return SHIPENV_OK;
+  if (!h->ev_caller) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_caller, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(h->ev_caller, st));
+  h->caller_pending = true;
+  return SHIPENV_OK;
+}
+
 int launch_reset(shipenv* h, const uint8_t* mask, const double* init, int do_init, int reinit, cudaStream_t st) {
   const int model = h->params.ship[0].model_kind;
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
                       ? senv_fast::launch_reset(view(h), model, mask, init, do_init, reinit, st)
                       : senv_strict::launch_reset(view(h), model, mask, init, do_init, reinit, st);
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "reset kernel launch: %s", cudaGetErrorString(e));
-  return SHIPENV_OK;
+  return note_caller_stream(h, st);
 }
 
 int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t st) {
@@ -149,6 +167,10 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   }
   int persistent = h->persist_mode;
   if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
+  // A launch of a few _step() per environment is a streaming pass over the state (HBM-bound, 704 B per env-step):
+  // one slot per environment, so that every warp loads and stores whole 256-byte row segments together and the block
+  // scheduler overlaps the CTAs' load / compute / store phases; the work queue only pays off for long calls.
+  if (mode == 1 && k <= SHIPENV_STREAMING_K) persistent = 0;
   if (h->time_kernels) {
     if (h->kernel_pending) {                 // fold the previous launch into the sum before reusing the events
       float ms = 0.f;
@@ -170,7 +192,7 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   // only the automatic grid policy reads the count of finished environments back
   if (h->persist_mode < 0)
     CUDA_TRY(cudaMemcpyAsync(h->done_host, h->queue_dev + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-  return SHIPENV_OK;
+  return note_caller_stream(h, st);
 }
 
 // ---- culling grid ------------------------------------------------------------------------------
@@ -261,14 +283,34 @@ int build_grid(shipenv* h) {
           edges[((size_t)iy * nx + ix) * 2 + (i >> 6)] |= 1ull << (i & 63);
       }
     }
-  if (h->grid_dev) cudaFree(h->grid_dev);
-  h->grid_dev = nullptr;
-  CUDA_TRY(cudaMalloc(&h->grid_dev, cells.size() * sizeof(unsigned)));
-  CUDA_TRY(cudaMemcpy(h->grid_dev, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
-  if (h->edges_dev) cudaFree(h->edges_dev);
-  CUDA_TRY(cudaMalloc(&h->edges_dev, edges.size() * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemcpy(h->edges_dev, edges.data(), edges.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  // allocate and fill the new tables first; the handle keeps its old ones if anything fails
+  unsigned* cells_dev = nullptr;
+  unsigned long long* edges_dev = nullptr;
+  cudaError_t e = cudaMalloc(&cells_dev, cells.size() * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&edges_dev, edges.size() * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemcpy(cells_dev, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(edges_dev, edges.data(), edges.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(cells_dev);
+    cudaFree(edges_dev);
+    return fail(SHIPENV_E_CUDA, "uploading the map culling grid: %s", cudaGetErrorString(e));
+  }
+  cudaFree(h->grid_dev);
+  cudaFree(h->edges_dev);
+  h->grid_dev = cells_dev;
+  h->edges_dev = edges_dev;
   h->grid = SenvGrid{h->grid_dev, h->edges_dev, p.map_min_e, p.map_min_n, 1.0 / cell, (double)nx, (double)ny, nx, ny};
+  return SHIPENV_OK;
+}
+
+// (re)build the kernels' shared-memory block from the uploaded parameters, with the device code of the handle's build
+int build_staged(shipenv* h) {
+  if (!h->staged_dev) CUDA_TRY(cudaMalloc(&h->staged_dev, senv_fast::staged_bytes()));
+  CUDA_TRY((h->params.math_mode == SHIPENV_MATH_FAST)
+               ? senv_fast::launch_build_staged(h->params_dev, h->staged_dev, nullptr)
+               : senv_strict::launch_build_staged(h->params_dev, h->staged_dev, nullptr));
+  CUDA_TRY(cudaStreamSynchronize(nullptr));
   return SHIPENV_OK;
 }
 
@@ -285,7 +327,13 @@ __global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, doubl
 }
 
 int ensure_staging(shipenv* h) {
-  if (h->pinned) return SHIPENV_OK;
+  if (h->pinned) {
+    if (h->caller_pending) {                // order this call after what the caller submitted on its own stream
+      CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_caller, 0));
+      h->caller_pending = false;
+    }
+    return SHIPENV_OK;
+  }
   const size_t B = (size_t)h->num_envs;
   // actions f64 | obs 8 x f32 | reward f64 | info i32 | nsub i32 | mask u8
   h->pinned_bytes = B * (8 + 32 + 8 + 4 + 4 + 1) + 64;
@@ -293,6 +341,10 @@ int ensure_staging(shipenv* h) {
   CUDA_TRY(cudaMalloc(&h->act_dev, B * sizeof(double)));
   CUDA_TRY(cudaMalloc(&h->mask_dev, B));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (h->caller_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_caller, 0));
+    h->caller_pending = false;
+  }
   return SHIPENV_OK;
 }
 
@@ -313,21 +365,17 @@ Pinned pinned_view(shipenv* h) {
   return v;
 }
 
-// Is [ptr, ptr + bytes) page-locked?  Buffers of at least 256 KiB are registered on first use (callers such as
-// a rollout loop pass the same arrays every step, so the registration is paid once); small or unregistrable
-// buffers go through the pinned staging area instead.
+// Is [ptr, ptr + bytes) inside a range the caller page-locked through shipenv_register_host?  Only then do the
+// *_host copies go straight between the caller's memory and the device; every other buffer is staged through the
+// handle's own pinned area.  (The library never registers caller memory on its own: a registration outlives the
+// array it was made for, and a later allocation at the same address would be DMA'd through a stale mapping.)
 bool host_locked(shipenv* h, const void* ptr, size_t bytes) {
-  for (const auto& r : h->host_regs)
-    if (r.ptr == ptr && r.bytes >= bytes) return r.ok;
-  bool ok = false;
-  if (bytes >= (256u << 10) && h->host_regs.size() < 64) {
-    cudaError_t e = cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault);
-    if (e == cudaSuccess) ok = true;
-    else if (e == cudaErrorHostMemoryAlreadyRegistered) { ok = true; cudaGetLastError(); }
-    else cudaGetLastError();   // not registrable (e.g. read-only mapping): use the staging path
+  const char* p = static_cast<const char*>(ptr);
+  for (const auto& r : h->host_regs) {
+    const char* b = static_cast<const char*>(r.ptr);
+    if (p >= b && p + bytes <= b + r.bytes) return true;
   }
-  if (h->host_regs.size() < 64) h->host_regs.push_back({ptr, bytes, ok});
-  return ok;
+  return false;
 }
 
 int fetch_outputs(shipenv* h, float* obs_host, double* reward_host, int32_t* info_host, int32_t* nsub_host) {
@@ -384,17 +432,23 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
     return fail(SHIPENV_E_CUDA, "uploading parameters: %s", cudaGetErrorString(ce));
   }
   rc = build_grid(h);
+  if (rc == SHIPENV_OK) rc = build_staged(h);
   if (rc == SHIPENV_OK && (cudaMalloc(&h->queue_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
                            cudaMallocHost(&h->done_host, sizeof(unsigned long long)) != cudaSuccess))
     rc = fail(SHIPENV_E_CUDA, "allocating the work-queue counters failed");
   if (rc) {
     cudaFree(h->params_dev);
+    cudaFree(h->staged_dev);
     cudaFree(h->grid_dev);
+    cudaFree(h->edges_dev);
+    cudaFree(h->queue_dev);
+    if (h->done_host) cudaFreeHost(h->done_host);
+    cudaGetLastError();
     delete h;
     return rc;
   }
   *h->done_host = 0;
-  if (const char* pm = getenv("SHIPENV_PERSISTENT")) h->persist_mode = atoi(pm);   // -1 auto (default), 0, 1
+  if (const char* pm = getenv("SHIPENV_PERSISTENT")) h->persist_mode = atoi(pm);   // 1 (default), 0, -1 auto
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return SHIPENV_OK;
@@ -409,6 +463,7 @@ int shipenv_destroy(shipenv_t* h) {
     cudaFree(h->buf.info_i32); cudaFree(h->buf.nsub_i32); cudaFree(h->buf.counters);
   }
   cudaFree(h->params_dev);
+  cudaFree(h->staged_dev);
   cudaFree(h->grid_dev);
   cudaFree(h->edges_dev);
   cudaFree(h->queue_dev);
@@ -418,9 +473,10 @@ int shipenv_destroy(shipenv_t* h) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->ev_k0) { cudaEventDestroy(h->ev_k0); cudaEventDestroy(h->ev_k1); }
+  if (h->ev_caller) cudaEventDestroy(h->ev_caller);
   for (const auto& r : h->host_regs)
-    if (r.ok) cudaHostUnregister(const_cast<void*>(r.ptr));
-  cudaGetLastError();   // a buffer the caller already freed / unregistered is not an error of destroy
+    if (r.owned) cudaHostUnregister(const_cast<void*>(r.ptr));
+  cudaGetLastError();   // a range the caller already freed is not an error of destroy
   delete h;
   return SHIPENV_OK;
 }
@@ -461,19 +517,29 @@ int shipenv_alloc(shipenv_t* h) {
   CUDA_TRY(cudaSetDevice(h->device));
   ShipEnvLayout L;
   shipenv_layout(h, &L);
-  CUDA_TRY(cudaMalloc(&h->buf.ship_f64, L.ship_f64 * 8));
-  CUDA_TRY(cudaMalloc(&h->buf.ship_i32, L.ship_i32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.env_f64, L.env_f64 * 8));
-  CUDA_TRY(cudaMalloc(&h->buf.env_i32, L.env_i32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.iw_f64, L.iw_f64 * 8));
-  CUDA_TRY(cudaMalloc(&h->buf.prev_f32, L.prev_f32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.obs_f32, L.obs_f32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.reward, L.reward * 8));
-  CUDA_TRY(cudaMalloc(&h->buf.info_i32, L.info_i32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.nsub_i32, L.nsub_i32 * 4));
-  CUDA_TRY(cudaMalloc(&h->buf.counters, L.counters * 8));
-  CUDA_TRY(cudaMemset(h->buf.counters, 0, L.counters * 8));
-  CUDA_TRY(cudaMemset(h->buf.iw_f64, 0, L.iw_f64 * 8));
+  ShipEnvBuffers b{};
+  cudaError_t e = cudaMalloc(&b.ship_f64, L.ship_f64 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b.ship_i32, L.ship_i32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.env_f64, L.env_f64 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b.env_i32, L.env_i32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.iw_f64, L.iw_f64 * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b.prev_f32, L.prev_f32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.obs_f32, L.obs_f32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.reward, L.reward * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&b.info_i32, L.info_i32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.nsub_i32, L.nsub_i32 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&b.counters, L.counters * 8);
+  if (e == cudaSuccess) e = cudaMemset(b.counters, 0, L.counters * 8);
+  if (e == cudaSuccess) e = cudaMemset(b.iw_f64, 0, L.iw_f64 * 8);
+  if (e != cudaSuccess) {
+    cudaFree(b.ship_f64); cudaFree(b.ship_i32); cudaFree(b.env_f64); cudaFree(b.env_i32); cudaFree(b.iw_f64);
+    cudaFree(b.prev_f32); cudaFree(b.obs_f32); cudaFree(b.reward); cudaFree(b.info_i32); cudaFree(b.nsub_i32);
+    cudaFree(b.counters);
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? SHIPENV_E_NOMEM : SHIPENV_E_CUDA, "allocating the state buffers: %s",
+                cudaGetErrorString(e));
+  }
+  h->buf = b;
   h->bound = true;
   h->owns = true;
   return SHIPENV_OK;
@@ -490,11 +556,23 @@ int shipenv_set_params(shipenv_t* h, const ShipEnvParams* params) {
   if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
   int rc = validate(params, h->num_envs);
   if (rc) return rc;
+  if (h->constructed) {
+    // the state buffers hold environments of one model class / env class / route length: a parameter update may
+    // change numbers (gains, time steps, the dt_shaft of the reset quirk, the map), not what the state means
+    if (params->ship[0].model_kind != h->params.ship[0].model_kind || params->env_kind != h->params.env_kind ||
+        params->ship[0].n_wp != h->params.ship[0].n_wp || params->ship[1].n_wp != h->params.ship[1].n_wp ||
+        params->max_sampling_frequency != h->params.max_sampling_frequency || params->math_mode != h->params.math_mode)
+      return fail(SHIPENV_E_STATE, "model_kind, env_kind, route lengths, max_sampling_frequency and math_mode cannot "
+                                   "change once the environments are constructed: create a new handle");
+  }
   CUDA_TRY(cudaSetDevice(h->device));
-  h->params = *params;
   CUDA_TRY(cudaDeviceSynchronize());   // kernels in flight on any stream may still read the old block
+  const ShipEnvParams old = h->params;
+  h->params = *params;
+  rc = build_grid(h);                  // (keeps the old grid when it fails)
+  if (rc) { h->params = old; return rc; }
   CUDA_TRY(cudaMemcpy(h->params_dev, params, sizeof(ShipEnvParams), cudaMemcpyHostToDevice));
-  return build_grid(h);
+  return build_staged(h);
 }
 
 int shipenv_construct(shipenv_t* h, const double* init_dev, void* stream) {
@@ -561,7 +639,7 @@ int shipenv_ship_rollout(shipenv_t* h, int k, void* stream) {
   const int model = h->params.ship[0].model_kind;
   CUDA_TRY((h->params.math_mode == SHIPENV_MATH_FAST) ? senv_fast::launch_rollout(view(h), model, k, st)
                                                       : senv_strict::launch_rollout(view(h), model, k, st));
-  return SHIPENV_OK;
+  return note_caller_stream(h, st);
 }
 
 int shipenv_reset_host(shipenv_t* h, const uint8_t* mask_host, float* obs_host) {
@@ -614,6 +692,38 @@ int shipenv_substeps_host(shipenv_t* h, int k, float* obs_host, double* reward_h
   return fetch_outputs(h, obs_host, reward_host, info_host, nsub_host);
 }
 
+int shipenv_register_host(shipenv_t* h, void* ptr, size_t bytes) {
+  if (!h || !ptr || bytes == 0) return fail(SHIPENV_E_ARG, "bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (const auto& r : h->host_regs)
+    if (r.ptr == ptr && r.bytes >= bytes) return SHIPENV_OK;
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  bool owned = true;
+  if (e == cudaErrorHostMemoryAlreadyRegistered) {   // page-locked by someone else (e.g. torch pin_memory): usable, not ours
+    cudaGetLastError();
+    owned = false;
+  } else if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(SHIPENV_E_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+  }
+  h->host_regs.push_back({ptr, bytes, owned});
+  return SHIPENV_OK;
+}
+
+int shipenv_unregister_host(shipenv_t* h, void* ptr) {
+  if (!h || !ptr) return fail(SHIPENV_E_ARG, "bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  for (size_t i = 0; i < h->host_regs.size(); ++i)
+    if (h->host_regs[i].ptr == ptr) {
+      if (h->stream) cudaStreamSynchronize(h->stream);     // no copy of ours is still using the range
+      if (h->host_regs[i].owned) cudaHostUnregister(ptr);
+      cudaGetLastError();
+      h->host_regs.erase(h->host_regs.begin() + (long)i);
+      return SHIPENV_OK;
+    }
+  return fail(SHIPENV_E_ARG, "range was not registered through shipenv_register_host");
+}
+
 int shipenv_set_trajectory_log(shipenv_t* h, double* log_dev, int32_t* count_dev, int64_t log_envs, int64_t capacity) {
   if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
   if (!log_dev || !count_dev || log_envs <= 0 || capacity <= 0) {
@@ -661,6 +771,21 @@ int shipenv_read_counters(shipenv_t* h, unsigned long long* out_host) {
   if (!h->buf.counters) return fail(SHIPENV_E_STATE, "no counters buffer bound");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaMemcpy(out_host, h->buf.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SHIPENV_OK;
+}
+
+int shipenv_map_query(shipenv_t* h, int64_t n, const double* north_dev, const double* east_dev, double ship_length,
+                      int32_t* contains_dev, int32_t* square_dev, double* distance_dev, void* stream) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  if (n <= 0 || !north_dev || !east_dev || !contains_dev || !square_dev || !distance_dev)
+    return fail(SHIPENV_E_ARG, "bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY((h->params.math_mode == SHIPENV_MATH_FAST)
+               ? senv_fast::launch_map_query(view(h), n, north_dev, east_dev, ship_length, contains_dev, square_dev,
+                                             distance_dev, st)
+               : senv_strict::launch_map_query(view(h), n, north_dev, east_dev, ship_length, contains_dev, square_dev,
+                                               distance_dev, st));
   return SHIPENV_OK;
 }
 

@@ -38,6 +38,9 @@
 #ifndef SENV_MIN_BLOCKS
 #define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
 #endif
+#ifndef SENV_ENV_BLOCK
+#define SENV_ENV_BLOCK 128  // threads per CTA of the env kernel
+#endif
 
 namespace SENV_NS {
 
@@ -179,19 +182,46 @@ __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship&
 // env kernel's culling-grid lookup) before the ~100 instructions of kinetics instead of after them.
 struct NoStepHook { __device__ __forceinline__ void operator()(double, double) const {} };
 
-template <int MODEL, class Hook = NoStepHook>
+// NavigationSystem.next_wpt (LOS_guidance.py:83-98): the waypoint switch at the top of the autopilot call.
+__device__ __forceinline__ bool wpt_reached(const Derived& H, const Ship& s) {
+  const double dn = s.wn - s.north, de = s.we - s.east;
+  return (dn * dn + de * de <= H.los_ra2) && (s.n_wp > s.k + 1);
+}
+
+// The step is written as ONE basic block from the LOS guidance to the derivatives: the simulator loop is bound by
+// the latency of its dependent FP64 chains (8 cycles per link), and the two long ones -- cross-track error -> root
+// -> division -> atan -> heading PID -> rudder forces, and sincos(psi) -> kinematics -> current / wind -> root ->
+// kinetics -- are independent until the force balance, so the scheduler can overlap them when no branch lies
+// between them (profiles/r02_ncu_summary.md).  Hence:
+//   SWITCH_AT_TOP = false: the caller performs the waypoint switch (wpt_reached + refresh_segment) after the
+//     previous step's integration -- the same position the reference tests at the top of this step -- inside its
+//     rarely taken event path, instead of a branch in front of every step;
+//   COLLAV_SIMPLE: the 'simple' collision avoidance block exists only in the instantiations that need it;
+//   the trajectory-log stores (a run-time option) sit behind everything else, right before the Euler update.
+template <int MODEL, bool SWITCH_AT_TOP = true, bool COLLAV_SIMPLE = false, class Hook = NoStepHook>
 __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Route& rt, int n_iw, Ship& s,
                                           bool collav_hit, double collav_bias, double heading_offset,
                                           double speed_factor, double* log_row = nullptr, Hook hook = Hook(),
                                           double2* yaw_sc = nullptr) {
   const Derived& H = derived_of(P);   // the step's parameters in reading order (see Derived)
   // --- NavigationSystem.next_wpt
-  {
-    const double dn = s.wn - s.north, de = s.we - s.east;
-    if (dn * dn + de * de <= H.los_ra2) {
-      if (s.n_wp > s.k + 1) { s.k += 1; refresh_segment(rt, n_iw, s); }
-    }
+  if (SWITCH_AT_TOP) {
+    if (wpt_reached(H, s)) { s.k += 1; refresh_segment(rt, n_iw, s); }
   }
+  // --- kinematics
+  double spsi, cpsi;
+  // yaw_sc (optional): sin / cos of the heading carried from the previous step -- the caller needs them for the
+  // heading the step ends with (the encounter type of the AST reward), and that heading is the next step's input
+  if (yaw_sc) { spsi = yaw_sc->x; cpsi = yaw_sc->y; }
+  else senv_sincos(s.yaw, &spsi, &cpsi);
+  const double u = s.u, v = s.v, r = s.r;
+  const double dt = H.dt;
+  const double d_north = cpsi * u + (-spsi) * v;
+  const double d_east = spsi * u + cpsi * v;
+  const double new_north = s.north + d_north * dt, new_east = s.east + d_east * dt, new_yaw = s.yaw + r * dt;
+  hook(new_north, new_east);
+  double2 new_sc = make_double2(0.0, 1.0);
+  if (yaw_sc) senv_sincos(new_yaw, &new_sc.x, &new_sc.y);
   // --- NavigationSystem.los_guidance
   const double heading_ref = los_guidance(P, s);
   // --- heading PID -> rudder angle
@@ -242,30 +272,12 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
     cmd = sat(error2 * H.kp_shaft_speed + error2_i * H.ki_shaft_speed, 0.0, 1.1);
   }
   // --- collav 'simple' (run_colav env.py:1189-1202, rl_env env.py:405-418)
-  if (collav_hit) {
+  if (COLLAV_SIMPLE && collav_hit) {
     cmd *= 0.5;
     cmd = (cmd < 0.0) ? 0.0 : ((cmd > 1.1) ? 1.1 : cmd);
     rudder += collav_bias;
     rudder = (rudder < -H.max_rudder) ? -H.max_rudder : ((rudder > H.max_rudder) ? H.max_rudder : rudder);
   }
-  // --- store_simulation_data (ship_model.py:418-429): the row is logged before the integration
-  if (log_row) {
-    log_row[SHIPENV_LOG_TIME] = s.time; log_row[SHIPENV_LOG_NORTH] = s.north; log_row[SHIPENV_LOG_EAST] = s.east;
-    log_row[SHIPENV_LOG_YAW] = s.yaw; log_row[SHIPENV_LOG_RUDDER] = rudder; log_row[SHIPENV_LOG_U] = s.u;
-    log_row[SHIPENV_LOG_V] = s.v; log_row[SHIPENV_LOG_R] = s.r; log_row[SHIPENV_LOG_OMEGA] = s.omega;
-    log_row[SHIPENV_LOG_CMD] = cmd; log_row[SHIPENV_LOG_E_CT] = s.e_ct;
-    log_row[SHIPENV_LOG_E_PSI] = fabs(s.yaw - heading_ref);            // get_heading_error, controllers.py:396-397
-  }
-  // --- kinematics
-  double spsi, cpsi;
-  // yaw_sc (optional): sin / cos of the heading carried from the previous step -- the caller needs them for the
-  // heading the step ends with (the encounter type of the AST reward), and that heading is the next step's input
-  if (yaw_sc) { spsi = yaw_sc->x; cpsi = yaw_sc->y; }
-  else senv_sincos(s.yaw, &spsi, &cpsi);
-  const double u = s.u, v = s.v, r = s.r;
-  const double d_north = cpsi * u + (-spsi) * v;
-  const double d_east = spsi * u + cpsi * v;
-  hook(s.north + d_north * H.dt, s.east + d_east * H.dt);
   // --- machinery
   double thrust, d_omega = 0.0;
   if (MODEL == SHIPENV_MODEL_SIMPLE) {
@@ -345,17 +357,24 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double d_u = H.inv_m_u * f0;
   const double d_v = H.inv_m_v * f1;
   const double d_r = H.inv_m_r * f2;
+  // --- store_simulation_data (ship_model.py:418-429): the row holds the state before the integration
+  if (log_row) {
+    log_row[SHIPENV_LOG_TIME] = s.time; log_row[SHIPENV_LOG_NORTH] = s.north; log_row[SHIPENV_LOG_EAST] = s.east;
+    log_row[SHIPENV_LOG_YAW] = s.yaw; log_row[SHIPENV_LOG_RUDDER] = rudder; log_row[SHIPENV_LOG_U] = s.u;
+    log_row[SHIPENV_LOG_V] = s.v; log_row[SHIPENV_LOG_R] = s.r; log_row[SHIPENV_LOG_OMEGA] = s.omega;
+    log_row[SHIPENV_LOG_CMD] = cmd; log_row[SHIPENV_LOG_E_CT] = s.e_ct;
+    log_row[SHIPENV_LOG_E_PSI] = fabs(s.yaw - heading_ref);            // get_heading_error, controllers.py:396-397
+  }
   // --- forward Euler
-  const double dt = H.dt;
-  s.north = s.north + d_north * dt;
-  s.east = s.east + d_east * dt;
-  s.yaw = s.yaw + r * dt;
+  s.north = new_north;
+  s.east = new_east;
+  s.yaw = new_yaw;
   s.u = s.u + d_u * dt;
   s.v = s.v + d_v * dt;
   s.r = s.r + d_r * dt;
   if (MODEL != SHIPENV_MODEL_SIMPLE) s.omega = s.omega + d_omega * H.dt_shaft;
   s.time = s.time + dt;
-  if (yaw_sc) senv_sincos(s.yaw, &yaw_sc->x, &yaw_sc->y);
+  if (yaw_sc) *yaw_sc = new_sc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -755,7 +774,10 @@ __device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P)
   return *reinterpret_cast<const Derived*>(reinterpret_cast<const char*>(&P) + kOffset);
 }
 
-__device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParams* gp) {
+// Builds the block from the parameters: bounding boxes, ring successors, the per-ship derived constants, SBMPC's
+// 1 / t table and the bearing tables of the file routes (64 atan2 + sincos).  Runs ONCE per parameter upload
+// (k_build_staged, from shipenv_create / shipenv_set_params); the kernels' CTAs copy the finished block.
+__device__ __forceinline__ void build_staged(SharedBlock& sb, const ShipEnvParams* gp) {
   const unsigned long long* src = reinterpret_cast<const unsigned long long*>(gp);
   unsigned long long* dst = reinterpret_cast<unsigned long long*>(&sb.p);
   constexpr int words = sizeof(ShipEnvParams) / 8;
@@ -851,6 +873,41 @@ __device__ __forceinline__ void stage_params(SharedBlock& sb, const ShipEnvParam
     }
   }
   __syncthreads();
+}
+
+static_assert(sizeof(SharedBlock) % 16 == 0, "the staged block is moved as one 16-byte-granular bulk copy");
+
+__global__ void __launch_bounds__(128) k_build_staged(const ShipEnvParams* gp, SharedBlock* out) {
+  __shared__ SharedBlock sb;
+  build_staged(sb, gp);
+  const uint4* src = reinterpret_cast<const uint4*>(&sb);
+  uint4* dst = reinterpret_cast<uint4*>(out);
+  for (int i = threadIdx.x; i < (int)(sizeof(SharedBlock) / 16); i += blockDim.x) dst[i] = src[i];
+}
+
+// CTA prologue of every kernel: the finished block (11.9 KB) arrives as ONE bulk copy -- thread 0 arms an mbarrier
+// with the byte count and issues cp.async.bulk (the TMA engine moves the bytes), every thread waits on the barrier's
+// phase.  Before, each CTA of each launch re-derived the block (64 atan2 + sincos among it): fixed work that
+// dominated a one-step-per-launch kernel of 24 us.
+__device__ __forceinline__ void stage_params(SharedBlock& sb, const void* staged) {
+  __shared__ alignas(8) unsigned long long mbar;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar);
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(&sb);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((unsigned)sizeof(SharedBlock)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(staged), "r"((unsigned)sizeof(SharedBlock)), "r"(bar) : "memory");
+  }
+  __syncthreads();                                   // the barrier is initialised before anyone polls it
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_STAGED:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@!p bra WAIT_STAGED;\n"
+      "}\n" ::"r"(bar) : "memory");
 }
 
 // trajectory log (shipenv_set_trajectory_log): next row of ship `sidx`, or nullptr when the ship is not logged
@@ -966,7 +1023,7 @@ __global__ void __launch_bounds__(128)
 k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__ init_dev, int do_init_step,
         int reinit) {
   __shared__ SharedBlock sb;
-  stage_params(sb, dv.params);
+  stage_params(sb, dv.staged);
   const long long n_ships = 2 * dv.num_envs;
   const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= n_ships) return;
@@ -1155,11 +1212,23 @@ enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 #ifndef SENV_MIN_BLOCKS_SBMPC
 #define SENV_MIN_BLOCKS_SBMPC 4   // measured: 3 CTAs/SM (168 registers, fewer spills) speeds the inactive steps up but slows the evaluation
 #endif
-template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
-__global__ void __launch_bounds__(128, SBMPC ? SENV_MIN_BLOCKS_SBMPC : SENV_MIN_BLOCKS)
+template <int MODEL, int ENVKIND, int MODE, int COLLAV>
+#ifdef SENV_MAXNREG
+__global__ void __maxnreg__(SENV_MAXNREG)
+#else
+__global__ void __launch_bounds__(SENV_ENV_BLOCK, COLLAV == SHIPENV_COLLAV_SBMPC ? SENV_MIN_BLOCKS_SBMPC : SENV_MIN_BLOCKS)
+#endif
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
+  constexpr bool SBMPC = COLLAV == SHIPENV_COLLAV_SBMPC;
+  constexpr bool SIMPLE = COLLAV == SHIPENV_COLLAV_SIMPLE;
+  // (the collision-avoidance mode is a template parameter: its branches would otherwise split the simulator step's
+  //  basic block in every instantiation, see ship_step)
+  // Without SBMPC the waypoint switch of step t + 1 (NavigationSystem.next_wpt at the top of the autopilot call) is
+  // decided right after the integration of step t and carried out in the event path below; SBMPC's extra
+  // los_guidance call runs on the segment BEFORE the switch (quirk 2), so those instantiations keep it at the top.
+  constexpr bool EARLY_SWITCH = !SBMPC;
   __shared__ SharedBlock sb_static;
-  stage_params(sb_static, dv.params);
+  stage_params(sb_static, dv.staged);
   const int lane = (int)(threadIdx.x & 31);
   const int role_tid = (int)(threadIdx.x & 1);
   // The shared-memory addresses of the parameter block and of this lane's ship parameters are held in two
@@ -1184,7 +1253,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   const bool dynamic_route = IS_IW && role == 1;
   const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
   const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
-  const bool collav_lane = (G.collav == SHIPENV_COLLAV_SIMPLE) && (role == 0 || !IS_IW);
+  const bool collav_lane = SIMPLE && (role == 0 || !IS_IW);
   const double collav_bias = IS_RL ? (-15.0 * (kPi / 180.0)) : (15.0 * (kPi / 180.0));
   const double route_end_n = P.wp_north[P.n_wp - 1], route_end_e = P.wp_east[P.n_wp - 1];
 
@@ -1203,11 +1272,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   // previous position itself (LOG_NORTH / LOG_EAST rows of env_f64) and the surge speed before the integration
   // (obs[6]) are only needed when the environment is stored: they are written to a per-lane shared-memory slot.
   // ([field][thread]: a warp's 8-byte stores of one field are conflict-free)
-  __shared__ double lane_scratch[3][128];
+  __shared__ double lane_scratch[3][SENV_ENV_BLOCK];
   unsigned scratch_addr = (unsigned)__cvta_generic_to_shared(&lane_scratch[0][threadIdx.x]);
   asm volatile("" : "+r"(scratch_addr));
   double* const scratch_base = reinterpret_cast<double*>(__cvta_shared_to_generic(scratch_addr));
-  struct { double& log_n; double& log_e; double& u_pre; } scratch{scratch_base[0], scratch_base[128], scratch_base[256]};
+  struct { double& log_n; double& log_e; double& u_pre; } scratch{scratch_base[0], scratch_base[SENV_ENV_BLOCK], scratch_base[2 * SENV_ENV_BLOCK]};
   double pending_dist = 0.0;
   // rl_env, fast build: sin / cos of this ship's heading, carried from step to step (see ship_step's yaw_sc)
   constexpr bool CARRY_YAW_SC = IS_RL && (SENV_FAST_MATH != 0);
@@ -1277,7 +1346,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         sampling_count = *ei; ei += 2 * B;
         flags = *ei;
       }
-      if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+      if (SIMPLE) {
         ps_tn = dv.buf.prev_f32[0 * B + env]; ps_te = dv.buf.prev_f32[1 * B + env];
         ps_on = dv.buf.prev_f32[2 * B + env]; ps_oe = dv.buf.prev_f32[3 * B + env];
       }
@@ -1303,6 +1372,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
       if (lstate == LS_RUN) {
         load_segment_points(rt, n_iw, s);
+        // the waypoint switch the first step of this call starts with (the route may have grown since the store)
+        if (EARLY_SWITCH && !(has_stop_branch && s.stop) && wpt_reached(derived_of(P), s)) {
+          s.k += 1;
+          refresh_segment(rt, n_iw, s);
+        }
         tlog_n = log_begin(dv, env, sidx);
         if (CARRY_YAW_SC) senv_sincos(s.yaw, &yaw_sc.x, &yaw_sc.y);
       }
@@ -1390,16 +1464,17 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           hit = (dn * dn + de * de) < 9000000.0f;
         }
         const double pre_n = s.north, pre_e = s.east;
-        ship_step<MODEL>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
-                         log_next_row(dv, 2 * env + role, tlog_n),
-                         [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); },
-                         CARRY_YAW_SC ? &yaw_sc : nullptr);
-        if (role == 1 && IS_IW) {
-          if (flags & SHIPENV_FLAG_TRACKER) {
-            // travel tracker on the two last logged rows (env.py:526-534)
-            travel_dist += pending_dist;
-            travel_time += dt;
-          }
+        ship_step<MODEL, !EARLY_SWITCH, SIMPLE>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
+                                                log_next_row(dv, 2 * env + role, tlog_n),
+                                                [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); },
+                                                CARRY_YAW_SC ? &yaw_sc : nullptr);
+        if (IS_IW) {
+          // travel tracker on the two last logged rows of the obstacle ship (env.py:526-534); evaluated without a
+          // branch on the role (the test lane's copies are never read: a divergent branch would cost the same issue
+          // slots and end the step's basic block)
+          const bool track = (role == 1) && (flags & SHIPENV_FLAG_TRACKER);
+          travel_dist += track ? pending_dist : 0.0;
+          travel_time += track ? dt : 0.0;
           const double tn = s.north - pre_n, te = s.east - pre_e;
           pending_dist = SENV_SQRT(tn * tn + te * te);
         }
@@ -1437,6 +1512,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         const double rn = s.north - s.wn, re = s.east - s.we;
         if ((rn * rn + re * re) < sb.roa2) my_flags |= 32;
       }
+      // bit 64: this ship's autopilot will switch to its next waypoint at the top of the next step
+      if (EARLY_SWITCH && wpt_reached(D, s)) my_flags |= 64;
       if (IS_RL) {
         const double gd = map_distance(mp, s.north, s.east);
         const double aect = fabs(s.e_ct);
@@ -1458,7 +1535,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     if (running) {
       nsub += 1;
       const int t_flags = role == 0 ? my_flags : p_flags, o_flags = role == 1 ? my_flags : p_flags;
-      if (G.collav == SHIPENV_COLLAV_SIMPLE) {   // self.states = next_states (float32)
+      if (SIMPLE) {   // self.states = next_states (float32)
         const double t_n = role == 0 ? s.north : p_north, t_e = role == 0 ? s.east : p_east;
         const double o_n = role == 1 ? s.north : p_north, o_e = role == 1 ? s.east : p_east;
         ps_tn = (float)t_n; ps_te = (float)t_e; ps_on = (float)o_n; ps_oe = (float)o_e;
@@ -1501,7 +1578,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       // One test for the common simulator step of a step(action) call: main loop (stage 0), no event bit of either
       // ship, radius of acceptance not reached, no collision and (run_colav, whose `done` needs both stop flags) no
       // stop flag set.  Nothing below changes anything then except the reward accumulators.
-      const bool plain_step = (MODE == MODE_STEP) && (stage == 0) && (((t_flags | o_flags) & 63) == 0) &&
+      const bool plain_step = (MODE == MODE_STEP) && (stage == 0) && (((t_flags | o_flags) & 127) == 0) &&
                               !is_collision && (IS_RL || ((s.stop | p_stop) == 0));
       if (plain_step) {
         if (IS_RL) { acc_reward += r_total; out_reward = r_total; }
@@ -1586,6 +1663,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
         }
       }
+      // NavigationSystem.next_wpt of the next step (LOS_guidance.py:83-98), unless this ship stops stepping (a
+      // stopped ship's autopilot is not called again) or the environment is stored (the next call's route may differ:
+      // the test is repeated when it is loaded)
+      if (EARLY_SWITCH && (my_flags & 64) && !finalize && !(has_stop_branch && s.stop)) {
+        s.k += 1;
+        refresh_segment(rt, n_iw, s);
+      }
       }   // !plain_step
     }
     } while (!__any_sync(FULL_MASK, finalize || lstate == LS_FETCH));
@@ -1630,7 +1714,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
             *ef = sb_chi_last;
           }
           ei[SHIPENV_EI_FLAGS * B + env] = flags;
-          if (G.collav == SHIPENV_COLLAV_SIMPLE) {
+          if (SIMPLE) {
             dv.buf.prev_f32[0 * B + env] = ps_tn; dv.buf.prev_f32[1 * B + env] = ps_te;
             dv.buf.prev_f32[2 * B + env] = ps_on; dv.buf.prev_f32[3 * B + env] = ps_oe;
           }
@@ -1668,7 +1752,7 @@ template <int MODEL>
 __global__ void __launch_bounds__(128)
 k_ship_rollout(DevView dv, int k_steps) {
   __shared__ SharedBlock sb;
-  stage_params(sb, dv.params);
+  stage_params(sb, dv.staged);
   const long long n_ships = 2 * dv.num_envs;
   const long long sidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= n_ships) return;
@@ -1686,11 +1770,37 @@ k_ship_rollout(DevView dv, int k_steps) {
   if (dv.buf.counters) atomicAdd(&dv.buf.counters[2], (unsigned long long)k_steps);
 }
 
+// ------------------------------------------------------------------------------------------------
+// map geometry probe (shipenv_map_query): the env kernel's own geometry routines on caller-given points, so that
+// tests can pin them against exact arithmetic (tests/test_map_geometry.py).  One thread per point.
+//   contains[i]   PolygonObstacle.if_pos_inside_obstacles(north, east) (obstacle.py:126-129), as step()'s prologue
+//                 tests a sampled waypoint
+//   square[i]     is_pos_inside_obstacles (check_condition.py:48-78): any corner of the ship_length square inside
+//   distance[i]   PolygonObstacle.obstacles_distance (obstacle.py:138-141) where it is <= 1000 m (the reward's clip);
+//                 beyond the clip the value is only guaranteed to be > 1000 (possibly inf), see map_distance
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_map_query(DevView dv, long long n, const double* __restrict__ north, const double* __restrict__ east,
+            double ship_length, int* __restrict__ contains, int* __restrict__ square, double* __restrict__ distance) {
+  __shared__ SharedBlock sb;
+  stage_params(sb, dv.staged);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ShipEnvParams& G = sb.p;
+  const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
+  const double pn = north[i], pe = east[i];
+  const unsigned cell = map_cell_masks(mp, pn, pe);
+  contains[i] = map_contains(mp, cell & 0xffffu, pn, pe) ? 1 : 0;
+  square[i] = pos_inside_obstacles(mp, cell & 0xffffu, pn, pe, ship_length) ? 1 : 0;
+  distance[i] = map_distance(mp, pn, pe);
+}
+
 #ifndef SENV_ONLY_ONE
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (declared in shipenv_launch.h)
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlock = 128;
+constexpr int kEnvBlock = SENV_ENV_BLOCK;
 
 inline int ship_grid(const DevView& v) { return (int)((2 * v.num_envs + kBlock - 1) / kBlock); }
 
@@ -1712,28 +1822,32 @@ cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st) {
 
 // persistent grid: as many CTAs as are resident at once (queried per instantiation), never more than
 // the environments need
-template <int MODEL, int ENVKIND, int MODE, bool SBMPC>
+template <int MODEL, int ENVKIND, int MODE, int COLLAV>
 static void launch_env_inst2(const SenvView& v, const double* actions, int k, unsigned long long* queue,
                              int sm_count, int persistent, cudaStream_t st) {
   static int per_sm = 0;
   if (per_sm == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE, SBMPC>, kBlock, 0) != cudaSuccess || n < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE, COLLAV>, kEnvBlock, 0) != cudaSuccess || n < 1)
       n = SENV_MIN_BLOCKS;
     per_sm = n;
   }
-  const long long need = (2 * v.num_envs + kBlock - 1) / kBlock;
+  const long long need = (2 * v.num_envs + kEnvBlock - 1) / kEnvBlock;
   const long long resident = (long long)per_sm * (sm_count > 0 ? sm_count : 148);
   // persistent: resident CTAs only, lane pairs refill from the queue; otherwise one slot per environment
   const int grid = (int)((persistent && resident < need) ? resident : need);
-  k_env<MODEL, ENVKIND, MODE, SBMPC><<<grid, kBlock, 0, st>>>(v, actions, k, queue);
+  k_env<MODEL, ENVKIND, MODE, COLLAV><<<grid, kEnvBlock, 0, st>>>(v, actions, k, queue);
 }
 
 template <int MODEL, int ENVKIND, int MODE>
 static void launch_env_inst(const SenvView& v, const double* actions, int k, unsigned long long* queue,
                             int sm_count, int persistent, cudaStream_t st) {
-  if (v.sbmpc) launch_env_inst2<MODEL, ENVKIND, MODE, true>(v, actions, k, queue, sm_count, persistent, st);
-  else launch_env_inst2<MODEL, ENVKIND, MODE, false>(v, actions, k, queue, sm_count, persistent, st);
+  if (v.collav == SHIPENV_COLLAV_SBMPC)
+    launch_env_inst2<MODEL, ENVKIND, MODE, SHIPENV_COLLAV_SBMPC>(v, actions, k, queue, sm_count, persistent, st);
+  else if (v.collav == SHIPENV_COLLAV_SIMPLE)
+    launch_env_inst2<MODEL, ENVKIND, MODE, SHIPENV_COLLAV_SIMPLE>(v, actions, k, queue, sm_count, persistent, st);
+  else
+    launch_env_inst2<MODEL, ENVKIND, MODE, SHIPENV_COLLAV_NONE>(v, actions, k, queue, sm_count, persistent, st);
 }
 
 template <int MODEL, int MODE>
@@ -1787,6 +1901,20 @@ cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned 
   return cudaGetLastError();
 }
 
+size_t staged_bytes() { return sizeof(SharedBlock); }
+
+cudaError_t launch_build_staged(const ShipEnvParams* params_dev, void* staged_dev, cudaStream_t st) {
+  k_build_staged<<<1, 128, 0, st>>>(params_dev, reinterpret_cast<SharedBlock*>(staged_dev));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_map_query(const SenvView& v, long long n, const double* north, const double* east,
+                             double ship_length, int* contains, int* square, double* distance, cudaStream_t st) {
+  k_map_query<<<(int)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(v, n, north, east, ship_length, contains, square,
+                                                                   distance);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st) {
   if (model == SHIPENV_MODEL_SIMPLE) k_ship_rollout<SHIPENV_MODEL_SIMPLE><<<ship_grid(v), kBlock, 0, st>>>(v, k);
   else if (model == SHIPENV_MODEL_DETAILED) k_ship_rollout<SHIPENV_MODEL_DETAILED><<<ship_grid(v), kBlock, 0, st>>>(v, k);
@@ -1795,6 +1923,6 @@ cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st)
 }
 
 #else
-template __global__ void k_env<0, 1, 0, false>(DevView, const double*, int, unsigned long long*);
+template __global__ void k_env<0, 1, 0, 0>(DevView, const double*, int, unsigned long long*);
 #endif
 }  // namespace SENV_NS

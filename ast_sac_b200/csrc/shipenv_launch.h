@@ -25,10 +25,11 @@ struct SenvGrid {
 
 struct SenvView {
   const ShipEnvParams* params;
+  const void* staged;   // the kernels' shared-memory block, built once per parameter upload (launch_build_staged)
   ShipEnvBuffers buf;
   long long num_envs;
   SenvGrid grid;
-  int sbmpc;   // params->collav == SHIPENV_COLLAV_SBMPC (selects the kernel instantiation)
+  int collav;  // params->collav (selects the kernel instantiation)
   // optional trajectory log (shipenv_set_trajectory_log)
   double* log_f64;
   int32_t* log_count;
@@ -46,6 +47,11 @@ struct SenvView {
                          unsigned long long* queue, int sm_count, int persistent, int clear_queue,           \
                          cudaStream_t st);                                                                     \
   cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st);                            \
+  size_t staged_bytes();                                                                                       \
+  cudaError_t launch_build_staged(const ShipEnvParams* params_dev, void* staged_dev, cudaStream_t st);         \
+  cudaError_t launch_map_query(const SenvView& v, long long n, const double* north, const double* east,        \
+                               double ship_length, int* contains, int* square, double* distance,               \
+                               cudaStream_t st);                                                               \
   cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned long long* mismatches_dev,   \
                                    cudaStream_t st);                                                           \
   }

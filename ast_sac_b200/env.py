@@ -371,8 +371,9 @@ class BatchedShipEnv:
     def close(self):
         if getattr(self, "_handle", None) is not None:
             torch.cuda.synchronize(self._device)
-            L.load().shipenv_destroy(self._handle)
+            L.load().shipenv_destroy(self._handle)      # (releases the host registrations of _host_arrays)
             self._handle = None
+            self.__dict__.pop("_host_bufs", None)
 
     def __del__(self):
         try:
@@ -384,7 +385,7 @@ class BatchedShipEnv:
     def __getstate__(self):
         d = {k: v for k, v in self.__dict__.items() if k not in (
             "_handle", "_params", "ship_f64", "ship_i32", "env_f64", "env_i32", "iw_f64", "prev_f32", "obs_buf",
-            "reward_buf", "info_buf", "nsub_buf", "counters", "log_f64", "log_count", "_log_envs")}
+            "reward_buf", "info_buf", "nsub_buf", "counters", "log_f64", "log_count", "_log_envs", "_host_bufs")}
         d["_device"] = str(self._device)
         return d
 
@@ -605,34 +606,41 @@ class BatchedShipEnv:
         L.check(L.load().shipenv_ship_rollout(self._handle, int(k), self._stream_ptr()))
 
     # -- host-buffer path (numpy in / numpy out through the C ABI's *_host entry points) -----------
+    def _host_arrays(self):
+        """The env's own host arrays of the host-buffer path, page-locked once through shipenv_register_host (the env
+        owns them for its whole life, so the registration cannot outlive the memory; close() releases them)."""
+        if not hasattr(self, "_host_bufs"):
+            B = self.num_envs
+            bufs = dict(actions=np.empty(B, np.float64), obs=np.empty((B, 8), np.float32), reward=np.empty(B, np.float64),
+                        info=np.empty(B, np.int32), nsub=np.empty(B, np.int32), reset_obs=np.empty((B, 8), np.float32))
+            lib = L.load()
+            for a in bufs.values():
+                if a.nbytes >= (64 << 10):          # small buffers: staging is as fast as a direct copy
+                    L.check(lib.shipenv_register_host(self._handle, a.ctypes.data, a.nbytes))
+            self._host_bufs = bufs
+        return self._host_bufs
+
     def step_host(self, actions: np.ndarray):
+        """step(action) through host buffers: numpy actions in, numpy (obs, reward, info word, substeps) out.  The
+        returned arrays are the env's own buffers and are overwritten by the next call."""
         B = self.num_envs
-        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(-1)
+        hb = self._host_arrays()
+        a = np.asarray(actions, dtype=np.float64).reshape(-1)
         if a.size != B:
             raise ValueError(f"expected {B} actions")
-        if not hasattr(self, "_host_out"):
-            self._host_out = (np.empty((B, 8), np.float32), np.empty(B, np.float64), np.empty(B, np.int32),
-                              np.empty(B, np.int32))
-        obs, rew, info, nsub = self._host_out
-        torch.cuda.current_stream(self._device).synchronize()
-        L.check(L.load().shipenv_step_host(self._handle, a.ctypes.data, obs.ctypes.data, rew.ctypes.data,
-                                           info.ctypes.data, nsub.ctypes.data))
-        return obs, rew, info, nsub
+        np.copyto(hb["actions"], a)      # one persistent page-locked array instead of whatever the caller passed
+        L.check(L.load().shipenv_step_host(self._handle, hb["actions"].ctypes.data, hb["obs"].ctypes.data,
+                                           hb["reward"].ctypes.data, hb["info"].ctypes.data, hb["nsub"].ctypes.data))
+        return hb["obs"], hb["reward"], hb["info"], hb["nsub"]
 
     def reset_host(self, mask: Optional[np.ndarray] = None):
-        B = self.num_envs
         if not self._post_reset:
             self.reset()
-            torch.cuda.current_stream(self._device).synchronize()
-        if not hasattr(self, "_host_reset_obs"):
-            # one persistent array: the C ABI page-locks caller buffers it sees repeatedly
-            self._host_reset_obs = np.empty((B, 8), np.float32)
-        obs = self._host_reset_obs
+        obs = self._host_arrays()["reset_obs"]
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)
             mptr = mask.ctypes.data
-        torch.cuda.current_stream(self._device).synchronize()
         L.check(L.load().shipenv_reset_host(self._handle, mptr, obs.ctypes.data))
         return obs
 

@@ -32,7 +32,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("AST_SAC_REFERENCE", "/root/reference")
+def _find_reference_root() -> str:
+    """/root/reference in the build container; on the GPU box (where it does not exist) the byte-for-byte copy of its
+    simulator packages that oracle/build_ref.py puts into oracle/_ref/ (git-ignored, travels with the snapshot)."""
+    env = os.environ.get("AST_SAC_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/run_colav"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:
@@ -366,3 +377,42 @@ def make_rl_env(args: Args, **kw):
     assets, map_obj = build_rl_assets(args, **kw)
     from rl_env.ship_in_transit.env import MultiShipRLEnv
     return MultiShipRLEnv(assets=assets, map=map_obj, args=args), assets
+
+
+# --------------------------------------------------------------------------------------------
+# timing of the unmodified reference (bench.py cpu_baseline: "reference_python_1core")
+# --------------------------------------------------------------------------------------------
+def time_reference(workload: str = "colav_iw", collav: str = "none", min_steps: int = 2000, warmup_steps: int = 200,
+                   seed: int = 0):
+    """env-steps/s of the UNMODIFIED reference env on one host core (the reference is single-process Python):
+    episodes of reset() + 9 step(action) with scoping angles ~ U(-pi/6, pi/6), `warmup_steps` simulator steps
+    untimed, then whole step() calls until at least `min_steps` simulator steps are timed.
+    Returns (rate, steps, seconds).  One env-step = one _step() = one row of the ship's simulation log."""
+    import time
+    rng = np.random.default_rng(seed)
+    args = Args(time_step=4, collav_mode=collav)
+    env, assets = (make_rl_env(args) if workload == "rl" else make_colav_iw_env(args))
+    log = assets[1].ship_model.simulation_results
+
+    def rows():
+        return len(log['time [s]']) if 'time [s]' in log else 0
+
+    timed_steps, timed_s, warmed = 0, 0.0, 0
+    while timed_steps < min_steps:
+        env.reset()
+        log = assets[1].ship_model.simulation_results
+        for _ in range(9):
+            a = np.array([rng.uniform(-np.pi / 6, np.pi / 6)], dtype=np.float64)
+            n0 = rows()
+            t0 = time.perf_counter()
+            out = env.step(a)
+            dt = time.perf_counter() - t0
+            n = rows() - n0
+            if warmed < warmup_steps:
+                warmed += n
+            else:
+                timed_steps += n
+                timed_s += dt
+            if out[-2] or timed_steps >= min_steps:
+                break
+    return timed_steps / timed_s, timed_steps, timed_s

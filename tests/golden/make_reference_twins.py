@@ -8,8 +8,13 @@ Why: with ``measured_shaft_speed = forward_speed`` (rl_env/ship_in_transit/env.p
 controller (rl_env/ship_in_transit/sub_systems/controllers.py:185-189) has gain ~1e4 inside a 1e-4 m/s band, so two
 IEEE-correct evaluations of the reference's formulas that differ by one ulp somewhere (another libm, another BLAS)
 drift apart by more than 1e-9 for a few percent of the episodes.  How far is measured here ON THE REFERENCE ITSELF:
-every episode is re-run four times with one initial state of both ships moved by one ulp (surge speed up / down,
-heading up, shaft speed down), and the largest relative state difference to the unperturbed run after each
+every episode is re-run twelve times -- four twins with one initial state of both ships moved by one ulp (surge
+speed up / down, heading up, shaft speed down), four "other libm" twins in which the reference code runs unchanged
+on a math library whose sin / cos / arctan2 / atan results differ from the installed one by at most one ulp (what
+any other platform's IEEE-conformant libm does: glibc vs SVML vs CUDA), and four "other BLAS" twins in which
+np.dot / np.linalg.inv (the 3x3 products of three_dof_kinetics, rl_env ship_model.py:849-861) return results that
+differ by at most one ulp per element (OpenBLAS here vs the MKL of the reference's ast-sac.yml: FMA use and
+summation order are the library's choice) -- and the largest relative state difference to the stock run after each
 step(action) call is the episode's *reference envelope*.  The GPU tests accept min(1e-6, 10 x envelope) instead of
 1e-9 only where the envelope says so, and waive a flag only where a reference twin itself flips it.
 
@@ -65,8 +70,62 @@ def twin_inits(variant, test_init, obs_init):
     return ti, oi, tuple(om)
 
 
+N_VARIANTS = 13       # 0 stock, 1-4 one-ulp initial states, 5-8 other-libm twins, 9-12 other-BLAS twins
+
+
+class _JitterLib:
+    """numpy / math with the named transcendental functions moved by -1, 0 or +1 ulp (chosen by a hash of the
+    argument bits and the twin's seed): an equally valid (<= 1 ulp) math library beneath the unmodified reference."""
+
+    def __init__(self, base, names, seed):
+        self._base, self._seed = base, seed
+        for n in names:
+            setattr(self, n, self._wrap(getattr(base, n)))
+
+    def __getattr__(self, name):
+        return getattr(self._base, name)
+
+    def _wrap(self, fn):
+        seed = self._seed
+
+        def jittered(*args):
+            r = fn(*args)
+            if isinstance(r, np.ndarray):                       # np.dot / np.linalg.inv: every element by -1, 0, +1 ulp
+                rng = np.random.default_rng(hash((seed, r.tobytes())) & 0xffffffffffff)
+                d = rng.integers(-1, 2, size=r.shape)
+                out = np.where(d > 0, np.nextafter(r, np.inf), np.where(d < 0, np.nextafter(r, -np.inf), r))
+                return np.where(np.isfinite(r) & (r != 0), out, r)
+            h = hash((seed,) + tuple(float(a).hex() for a in args)) % 3
+            if h == 0 or not np.isfinite(r) or r == 0:
+                return r
+            out = np.nextafter(np.float64(r), np.inf if h == 1 else -np.inf)
+            return out if isinstance(r, np.floating) else float(out)
+        return jittered
+
+
 def run_episode(job):
     """One episode of the reference's MultiShipRLEnv; returns the per-call results as arrays."""
+    variant = job[-1]
+    if variant < 5:
+        return _run_episode(job)
+    import rl_env.ship_in_transit.sub_systems.LOS_guidance as M_los
+    import rl_env.ship_in_transit.sub_systems.ship_model as M_ship
+    saved = (M_ship.np, M_los.math)
+    import math
+    if variant < 9:
+        M_ship.np = _JitterLib(np, ("sin", "cos", "arctan2"), variant)
+        M_los.math = _JitterLib(math, ("atan", "atan2"), variant)
+    else:
+        blas = _JitterLib(np, ("dot",), variant)
+        blas.linalg = _JitterLib(np.linalg, ("inv",), variant)
+        M_ship.np = blas
+    try:
+        return _run_episode(job)
+    finally:
+        M_ship.np, M_los.math = saved
+
+
+def _run_episode(job):
     dt, collav, mode, sim_time, test_init, obs_init, actions, variant = job
     ti, oi, om = twin_inits(variant, test_init, obs_init)
     args = H.Args(time_step=dt, collav_mode=collav)
@@ -121,7 +180,7 @@ def golden_envelopes(pool):
         g = np.load(os.path.join(HERE, name + ".npz"))
         meta = json.loads(str(g["meta"]))
         acts = np.asarray(g["actions"], dtype=np.float64)[: int(g["n_valid"])]
-        for v in range(5):
+        for v in range(N_VARIANTS):
             jobs.append((meta["dt"], meta.get("collav", "none"), meta.get("mode", "PTI"), meta.get("sim_time", 10000),
                          meta.get("test_init"), meta.get("obs_init"), acts, v))
             index.append((name, v))
@@ -161,7 +220,7 @@ def batch(pool, collav, B, seed_actions=0, seed_init=1, pos_jitter_m=100.0):
     for b in range(B):
         ti = dict(initial_north_position_m=float(init_np[0, b, 0]), initial_east_position_m=float(init_np[1, b, 0]))
         oi = dict(initial_north_position_m=float(init_np[0, b, 1]), initial_east_position_m=float(init_np[1, b, 1]))
-        for v in range(5):
+        for v in range(N_VARIANTS):
             jobs.append((4, collav, "PTI", 10000, ti, oi, actions[b], v))
     t0 = time.time()
     res = pool.map(run_episode, jobs, chunksize=1)
@@ -173,7 +232,7 @@ def batch(pool, collav, B, seed_actions=0, seed_init=1, pos_jitter_m=100.0):
                env_state=np.zeros((B, 9)), env_ctrl=np.zeros((B, 9)), env_reward=np.zeros((B, 9)),
                env_obs=np.zeros((B, 9)), env_travel=np.zeros((B, 9)), flags_equal=np.ones((B, 9), np.int32))
     for b in range(B):
-        runs = res[5 * b: 5 * b + 5]
+        runs = res[N_VARIANTS * b: N_VARIANTS * (b + 1)]
         base = runs[0]
         n = base["n_valid"]
         for k in ("states", "ctrl", "obs", "reward", "travel", "flags"):

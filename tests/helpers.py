@@ -57,18 +57,19 @@ def oracle_ctrl_vec(s, detailed: bool) -> np.ndarray:
 # reference envelopes (tests/golden/make_reference_twins.py): how far the UNMODIFIED reference's own trajectory
 # moves when one initial state changes by one ulp.  A detailed-model state may differ from the reference by
 # REL_TOL, or -- only where the reference's own one-ulp twins drift further than REL_TOL / 10 -- by
-# ENVELOPE_K x that drift, capped at ENVELOPE_CAP; where ONE ulp moves the reference itself by more than the cap
-# (3 of 64 SBMPC episodes: up to 4e-4) the bound is that drift itself, factor 1.  Flags are waived only where a
-# reference twin flips them.
+# ENVELOPE_K x that drift, capped at ENVELOPE_CAP; where ONE ulp moves the reference itself by more than a third of
+# the cap (4 of 64 SBMPC episodes: SBMPC picks another discrete behaviour and the twins part by up to 6 %) the bound
+# is ENVELOPE_K_CHAOTIC x that drift.  Flags are waived only where a reference twin flips them.
 # ------------------------------------------------------------------------------------------------
 ENVELOPE_K = 10.0
 ENVELOPE_CAP = 1e-6
+ENVELOPE_K_CHAOTIC = 3.0
 
 
 def envelope_tol(envelope: float, base: float = REL_TOL) -> float:
     """Tolerance of a comparison whose reference one-ulp envelope is `envelope`."""
     s = base / REL_TOL
-    return max(base, min(ENVELOPE_CAP * s, ENVELOPE_K * float(envelope) * s), float(envelope) * s)
+    return max(base, min(ENVELOPE_CAP * s, ENVELOPE_K * float(envelope) * s), ENVELOPE_K_CHAOTIC * float(envelope) * s)
 
 
 def golden_envelope(name: str):
