@@ -498,9 +498,11 @@ class BatchedShipEnv:
         return self.log_f64[i, :n].cpu().numpy()
 
     def simulation_results(self, role: int, env: int = 0) -> dict:
-        """The log of one ship under the reference's ``simulation_results`` keys and units (the state and
-        controller columns; the fuel / power bookkeeping columns of ship_model.py:911-937 are derived quantities
-        off the step path and are not reproduced)."""
+        """The log of one ship under the reference's ``simulation_results`` keys and units: the 12 state / controller
+        columns straight from the device log (ship_model.py:418-429) and, for ShipModelAST, the 15 machinery
+        bookkeeping columns of rl_env ship_model.py:911-937 (load split, powers, fuel rates and totals, motor
+        torque), which are functions of the logged load fraction and shaft speed and are derived on the host
+        (sim/ship_engine.py:bookkeeping_columns).  Same 27 keys, same order as the reference."""
         t = self.trajectory(role, env)
         c = {n: t[:, i] for i, n in enumerate(L.LOG_COLS)}
         deg = 180 / np.pi
@@ -512,7 +514,12 @@ class BatchedShipEnv:
         p = self._params.ship[role]
         if p.model_kind == L.MODEL_DETAILED:
             out['propeller shaft speed [rpm]'] = c["omega"] * 30 / np.pi
-            out['commanded load fraction [-]'] = c["cmd"]
+            # a row that repeats its predecessor except for the clock is a stopped ship's store_last_simulation_data
+            body = np.delete(t, L.LOG_COLS.index("time"), axis=1)
+            new_row = np.ones(len(t), dtype=bool)
+            new_row[1:] = np.any(body[1:] != body[:-1], axis=1)
+            mm = self.assets[role].ship_model.ship_machinery_model
+            out.update(mm.bookkeeping_columns(c["cmd"], c["omega"], p.dt_shaft, new_row))
             out['thrust force [kN]'] = p.thrust_coeff * c["omega"] * np.abs(c["omega"]) / 1000      # ship_engine.py:411-414
         elif p.model_kind == L.MODEL_SIMPLIFIED:
             out['commanded load fraction [-]'] = c["cmd"]

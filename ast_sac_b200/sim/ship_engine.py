@@ -126,6 +126,59 @@ class ShipMachineryModel:
         self.time_step = time_step
         self.int = _Integrator(dt=time_step)
         self._initial_parameters = {'omega': self.omega}
+        self.fuel_coeffs_for_main_engine = machinery_config.specific_fuel_consumption_coefficients_me
+        self.fuel_coeffs_for_diesel_gen = machinery_config.specific_fuel_consumption_coefficients_dg
+
+    def bookkeeping_columns(self, load_perc, omega, dt_machinery, new_row):
+        """The machinery bookkeeping columns of ShipModelAST.simulation_results (rl_env ship_model.py:911-937) from
+        the two logged quantities they are functions of -- the commanded load fraction and the shaft speed of every
+        log row -- evaluated with the reference's expressions in NumPy (post-processing of the device log, off the
+        step path): MachineryMode.distribute_load (ship_engine.py:46-76), fuel_consumption / spec_fuel_cons
+        (:250-295) and main_engine_torque (:416-423).
+
+        load_perc, omega: arrays over the log rows; dt_machinery: the machinery integrator's dt (0.01 after the
+        first reset(), ship_engine.py:331-333 -- the fuel totals are integrated with it); new_row: bool array, False
+        where the row repeats the previous one (store_last_simulation_data adds no fuel)."""
+        m = self.mode
+        lp = np.asarray(load_perc, dtype=np.float64)
+        w = np.asarray(omega, dtype=np.float64)
+        total = lp * m.available_propulsion_power
+        zeros = np.zeros_like(lp)
+        if m.shaft_generator_state == 'MOTOR':
+            me = np.minimum(total, m.main_engine_capacity)
+            el = total + self.hotel_load - me
+            pct_el = el / m.electrical_capacity
+            pct_me = zeros if m.main_engine_capacity == 0 else me / m.main_engine_capacity
+        elif m.shaft_generator_state == 'GEN':
+            el = zeros + min(self.hotel_load, m.electrical_capacity)
+            me = total + self.hotel_load - el
+            pct_me = me / m.main_engine_capacity
+            pct_el = zeros if m.electrical_capacity == 0 else el / m.electrical_capacity
+        else:
+            me = total
+            el = zeros + self.hotel_load
+            pct_me = me / m.main_engine_capacity
+            pct_el = el / m.electrical_capacity
+
+        def spec(pct, c):
+            return (c.a * pct ** 2 + c.b * pct + c.c) / 3.6e9
+        rate_me = np.where(me == 0, 0.0, me * spec(pct_me, self.fuel_coeffs_for_main_engine))
+        rate_el = np.where(pct_el == 0, 0.0, el * spec(pct_el, self.fuel_coeffs_for_diesel_gen))
+        gate = np.asarray(new_row, dtype=bool)
+        cons_me = np.cumsum(np.where(gate, rate_me * dt_machinery, 0.0))
+        cons_el = np.cumsum(np.where(gate, rate_el * dt_machinery, 0.0))
+        cons = np.cumsum(np.where(gate, (rate_me + rate_el) * dt_machinery, 0.0))
+        p_me = m.available_propulsion_power_main_engine
+        torque = np.minimum(lp * p_me / (w + 0.1), p_me / 5 * np.pi / 30)
+        return {
+            'commanded load fraction me [-]': pct_me, 'commanded load fraction hsg [-]': pct_el,
+            'power me [kw]': me / 1000, 'available power me [kw]': zeros + m.main_engine_capacity / 1000,
+            'power electrical [kw]': el / 1000, 'available power electrical [kw]': zeros + m.electrical_capacity / 1000,
+            'power [kw]': (el + me) / 1000, 'propulsion power [kw]': (lp * m.available_propulsion_power) / 1000,
+            'fuel rate me [kg/s]': rate_me, 'fuel rate hsg [kg/s]': rate_el, 'fuel rate [kg/s]': rate_me + rate_el,
+            'fuel consumption me [kg]': cons_me, 'fuel consumption hsg [kg]': cons_el, 'fuel consumption [kg]': cons,
+            'motor torque [Nm]': torque,
+        }
 
 
 class SimplifiedPropulsionMachinerySystemConfiguration(NamedTuple):   # ship_engine.py:148-157

@@ -342,8 +342,8 @@ def log_golden(kind):
         rows = np.unique(np.concatenate([np.arange(0, n, 7), np.arange(max(0, n - 60), n)]))
         out[f"{name}_n"] = n
         out[f"{name}_rows"] = rows
-        for k in LOG_KEYS:
-            if k in sr:
+        for k in sr:        # every key of simulation_results: 12 state / controller columns + the machinery bookkeeping
+            if len(sr[k]) == n:
                 out[f"{name}|{k}"] = np.asarray(sr[k], dtype=np.float64)[rows]
     return out
 

@@ -640,14 +640,17 @@ def test_trajectory_log_matches_reference_simulation_results(kind):
         sr = env.simulation_results(role, env=0)
         assert len(sr['time [s]']) == int(g[f"{name}_n"])
         rows = g[f"{name}_rows"]
+        # the same keys in the same order as the reference's simulation_results (27 for ShipModelAST: the 12 state /
+        # controller columns and the 15 machinery bookkeeping columns derived on the host, ship_model.py:911-937)
+        ref_keys = [k.split("|", 1)[1] for k in g.files if k.startswith(name + "|")]
+        assert list(sr.keys()) == ref_keys, (list(sr.keys()), ref_keys)
         for key in sr:
             gk = f"{name}|{key}"
-            if gk not in g.files:
-                assert key == 'commanded load fraction [-]'
-                continue
             got = np.asarray(sr[key])[rows]
             want = g[gk]
-            scale = {'yaw rate [deg/sec]': 1e-3 * 180 / np.pi}.get(key, 1.0)
+            scale = {'yaw rate [deg/sec]': 1e-3 * 180 / np.pi, 'fuel rate me [kg/s]': 1e-3, 'fuel rate hsg [kg/s]': 1e-3,
+                     'fuel rate [kg/s]': 1e-3, 'fuel consumption me [kg]': 1e-3, 'fuel consumption hsg [kg]': 1e-3,
+                     'fuel consumption [kg]': 1e-3}.get(key, 1.0)
             e = rel_err(got, want, scale)
             assert e.max() < (1e-8 if kind == "rl" else REL_TOL), (kind, name, key, e.max(), int(e.argmax()))
         # environment 1 logged the same episode; the whole-episode columns of the episode fixture agree row by row

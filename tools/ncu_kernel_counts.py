@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Measured per-env-step counts of the env kernel -> profiles/kernel_counts.json (read by bench.py).
+
+    ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,\\
+smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum \\
+        --clock-control none --import-source on -k regex:k_env -s 11 -c 2 -o prof  python bench.py --steps 1 ...
+    ncu -i prof.ncu-rep --page raw --csv > prof.raw.csv
+    python tools/ncu_kernel_counts.py --key colav_iw --raw prof.raw.csv --bench bench.json --skip 11 --envs 100000
+
+Per captured launch the executed FP64 flop (DFMA = 2, DADD = DMUL = 1; thread-level, predicated-on) and the DRAM
+bytes are divided by the simulator steps that launch executed (bench.py prints them per launch index as
+`launch_env_steps`; launch i of the capture is step() call (skip + i) mod 9 of an episode).  The file records the
+hash of the device sources the capture belongs to: bench.py refuses to quote a roofline fraction from counts taken
+on other code."""
+import argparse
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def col(hdr, row, name, default=None):
+    return float(row[hdr.index(name)].replace(",", "")) if name in hdr and row[hdr.index(name)] else default
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--key", required=True, help="colav_iw | rl | colav_iw+sbmpc | rl+sbmpc")
+    ap.add_argument("--raw", required=True)
+    ap.add_argument("--bench", required=True, help="bench.py JSON line of the same command (launch_env_steps)")
+    ap.add_argument("--skip", type=int, required=True, help="the -s value of the ncu capture (k_env launches skipped)")
+    ap.add_argument("--envs", type=int, required=True)
+    ap.add_argument("--source", default=None, help="name of the committed ncu summary the numbers come from")
+    a = ap.parse_args()
+    csv.field_size_limit(10 ** 9)
+    rows = list(csv.reader(open(a.raw)))
+    hdr, data = rows[0], rows[2:]
+    line = json.loads(open(a.bench).read().strip().split("\n")[-1])
+    if a.key in ("colav_iw", "rl") or "workloads" not in line:
+        steps_per_launch = line["launch_env_steps"][1:]
+    else:
+        raise SystemExit("run bench.py with --workload/--collav of the key so that launch_env_steps belongs to it")
+    out = []
+    for i, r in enumerate(data):
+        n = steps_per_launch[(a.skip + i) % 9]
+        cyc = col(hdr, r, "sm__cycles_elapsed.max")
+
+        def total(op):
+            v = col(hdr, r, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum")
+            if v is None:
+                v = col(hdr, r, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
+            return v
+        dfma, dadd, dmul = total("dfma"), total("dadd"), total("dmul")
+        dram = col(hdr, r, "dram__bytes_read.sum", 0.0) + col(hdr, r, "dram__bytes_write.sum", 0.0)
+        # ncu prints byte counts in the unit of the units row; normalise to bytes
+        unit = rows[1][hdr.index("dram__bytes_read.sum")] if "dram__bytes_read.sum" in hdr else "byte"
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        out.append({"env_steps": n, "fp64_inst_per_env_step": (dfma + dadd + dmul) / n,
+                    "flop_exec_per_env_step": (2 * dfma + dadd + dmul) / n, "dram_bytes": dram * scale,
+                    "pipe_fp64_pct": col(hdr, r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "issue_active_pct": col(hdr, r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "achieved_occupancy_pct": col(hdr, r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                    "threads_per_inst": col(hdr, r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                    "duration_us": col(hdr, r, "gpu__time_duration.sum")})
+    mean = lambda k: sum(o[k] for o in out) / len(out)
+    try:
+        d = json.load(open(bench.KERNEL_COUNTS))
+    except Exception:
+        d = {"kernels": {}}
+    h = bench.device_source_hash()
+    if d.get("source_hash") != h:
+        d = {"kernels": {}}                       # counts of other code are dropped, not mixed
+    d["source_hash"] = h
+    d["hashed_files"] = list(bench.DEVICE_SOURCES)
+    d["kernels"][a.key] = {
+        "flop_exec_per_env_step": round(mean("flop_exec_per_env_step"), 1),
+        "fp64_inst_per_env_step": round(mean("fp64_inst_per_env_step"), 1),
+        "dram_bytes_per_launch": round(mean("dram_bytes")), "envs": a.envs,
+        "pipe_fp64_pct": mean("pipe_fp64_pct"), "issue_active_pct": mean("issue_active_pct"),
+        "achieved_occupancy_pct": mean("achieved_occupancy_pct"), "threads_per_inst": mean("threads_per_inst"),
+        "launches": out, "source": a.source or os.path.basename(a.raw)}
+    json.dump(d, open(bench.KERNEL_COUNTS, "w"), indent=1)
+    print(json.dumps(d["kernels"][a.key], indent=1)[:800])
+
+
+if __name__ == "__main__":
+    main()
