@@ -619,10 +619,10 @@ class BatchedShipEnv:
         if not hasattr(self, "_host_bufs"):
             B = self.num_envs
             bufs = dict(actions=np.empty(B, np.float64), obs=np.empty((B, 8), np.float32), reward=np.empty(B, np.float64),
-                        info=np.empty(B, np.int32), nsub=np.empty(B, np.int32), reset_obs=np.empty((B, 8), np.float32))
+                        info=np.empty(B, np.int32), nsub=np.empty(B, np.int32))
             lib = L.load()
             for a in bufs.values():
-                if a.nbytes >= (64 << 10):          # small buffers: staging is as fast as a direct copy
+                if a.nbytes >= (16 << 10):          # small buffers: staging is as fast as a direct copy
                     L.check(lib.shipenv_register_host(self._handle, a.ctypes.data, a.nbytes))
             self._host_bufs = bufs
         return self._host_bufs
@@ -643,7 +643,7 @@ class BatchedShipEnv:
     def reset_host(self, mask: Optional[np.ndarray] = None):
         if not self._post_reset:
             self.reset()
-        obs = self._host_arrays()["reset_obs"]
+        obs = self._host_arrays()["obs"]      # the array step_host() returns too: one mapped observation buffer
         mptr = None
         if mask is not None:
             mask = np.ascontiguousarray(mask, dtype=np.uint8)

@@ -559,6 +559,40 @@ def test_host_buffer_entry_points_match_device_path():
     env_d.close(); env_h.close()
 
 
+def test_host_path_with_registered_arrays_matches_device_path():
+    """The host-buffer path at a size where the env page-locks its arrays (shipenv_register_host: the copies go
+    straight between them and the device).  Whole episode, then a masked reset and more calls, every output of every
+    call against the device path."""
+    B = 8192
+    args = S.get_env_args(time_step=4)
+    init = S.jittered_init_states(S.build_rl_assets(args)[0], B, pos_jitter_m=50.0, seed=21)
+    env_d, _ = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+    env_h, _ = S.prepare_multiship_rl_env(args, num_envs=B, init_states=init)
+    gen = np.random.default_rng(6)
+    actions = gen.uniform(-np.pi / 6, np.pi / 6, size=(B, 12))
+    def both(j):
+        env_d.step(torch.from_numpy(actions[:, j]).cuda())
+        obs, rew, info, nsub = env_h.step_host(actions[:, j])
+        _sync()
+        assert np.array_equal(obs, env_d.obs_buf.cpu().numpy()), j
+        assert np.array_equal(rew, env_d.reward_buf.cpu().numpy()), j
+        assert np.array_equal(info, env_d.info_buf.cpu().numpy()), j
+        assert np.array_equal(nsub, env_d.nsub_buf.cpu().numpy()), j
+
+    env_d.reset()
+    assert np.array_equal(env_h.reset_host(), env_d.obs_buf.cpu().numpy())
+    for j in range(9):
+        both(j)
+    assert bool(env_d.done_mask.all())
+    mask = np.zeros(B, dtype=bool)
+    mask[::3] = True
+    env_d.reset(mask=torch.from_numpy(mask).cuda())
+    assert np.array_equal(env_h.reset_host(mask), env_d.obs_buf.cpu().numpy())
+    for j in range(9, 12):
+        both(j)
+    env_d.close(); env_h.close()
+
+
 def test_c_abi_standalone_without_torch_buffers():
     """The library used as a plain C library: shipenv_alloc owns the device memory."""
     from ast_sac_b200 import env as E

@@ -36,7 +36,10 @@ def main():
     ap.add_argument("--ks", default="1,16,128")
     ap.add_argument("--substeps-total", type=int, default=256, help="_step() calls per environment in the substeps regime")
     ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--regimes", default="episode,substeps", help="comma list of: episode, substeps")
+    ap.add_argument("--no-warmup", action="store_true", help="single measured pass per point (ncu captures)")
     a = ap.parse_args()
+    regimes = a.regimes.split(",")
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -74,9 +77,12 @@ def main():
             for j in range(BN.N_RL_STEPS):
                 env.step(actions[:, j])
 
-        episode()                                              # warm-up (module load, first touch)
+        counts, stale = BN.kernel_counts(a.workload, "none")
+        flop_exec = None if (counts is None or stale) else counts["flop_exec_per_env_step"]
+        if not a.no_warmup or "episode" in regimes:
+            episode()                                          # warm-up (module load, first touch)
         best = None
-        for _ in range(a.repeats):
+        for _ in range(a.repeats if "episode" in regimes else 0):
             flush.fill_(1.0)
             c0 = env.total_substeps()
             if world > 1:
@@ -88,15 +94,18 @@ def main():
             steps, ms = reduce(env.total_substeps() - c0, s.elapsed_time(e))
             if best is None or steps / ms > best[0] / best[1]:
                 best = (steps, ms)
-        rate = best[0] / (best[1] * 1e-3)
-        if rank == 0:
-            tf = rate / world * BN.FLOP_EXEC[a.workload] / 1e12
+        if best is not None and rank == 0:
+            rate = best[0] / (best[1] * 1e-3)
+            tf = None if flop_exec is None else rate / world * flop_exec / 1e12
             print(json.dumps({"envs_total": total, "n_gpus": world, "regime": "episode", "workload": a.workload,
                               "env_steps_per_s": rate, "ms": best[1], "env_steps": best[0],
-                              "fp64_tflops_per_gpu": tf, "fp64_frac_of_peak": tf / peak, "fp64_peak_tflops": peak}), flush=True)
-        for k in [int(x) for x in a.ks.split(",")]:
+                              "fp64_tflops_per_gpu": tf, "fp64_frac_of_peak": None if tf is None else tf / peak,
+                              "fp64_peak_tflops": peak}), flush=True)
+        for k in ([int(x) for x in a.ks.split(",")] if "substeps" in regimes else []):
             n_launch = max(1, a.substeps_total // k)
-            env.reset(); env._step(k)
+            env.reset()
+            if not a.no_warmup:
+                env._step(k)
             best = None
             for _ in range(a.repeats):
                 env.reset()
@@ -116,11 +125,11 @@ def main():
                     best = (steps, ms)
             rate = best[0] / (best[1] * 1e-3)
             if rank == 0:
-                tf = rate / world * BN.FLOP_EXEC[a.workload] / 1e12
+                tf = None if flop_exec is None else rate / world * flop_exec / 1e12
                 gbs = rate / world * BN.BYTES_K1 / k / 1e9
                 print(json.dumps({"envs_total": total, "n_gpus": world, "regime": f"substeps k={k}", "workload": a.workload,
                                   "launches": n_launch, "env_steps_per_s": rate, "ms": best[1], "env_steps": best[0],
-                                  "fp64_tflops_per_gpu": tf, "fp64_frac_of_peak": tf / peak,
+                                  "fp64_tflops_per_gpu": tf, "fp64_frac_of_peak": None if tf is None else tf / peak,
                                   "hbm_gbs_per_gpu": gbs, "hbm_frac_of_peak": gbs / hbm}), flush=True)
         env.close()
         del env
