@@ -15,7 +15,7 @@
 #include "shipenv_launch.h"
 
 #ifndef SHIPENV_STREAMING_K
-#define SHIPENV_STREAMING_K 8
+#define SHIPENV_STREAMING_K 0
 #endif
 
 namespace {
@@ -51,6 +51,7 @@ struct shipenv {
   const double* init_dev = nullptr;   // per-ship initial states given to shipenv_construct (caller-owned)
   unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch
   unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
+  int streaming_k = SHIPENV_STREAMING_K;    // _step() launches of at most this many steps use a static grid
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
   // CUDA events around the env kernel itself (k_env), for shipenv_env_kernel_ms: the step() / _step() entry
   // points also launch the prologue kernel and a memset, which a caller's own events would include
@@ -167,10 +168,10 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   }
   int persistent = h->persist_mode;
   if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
-  // A launch of a few _step() per environment is a streaming pass over the state (HBM-bound, 704 B per env-step):
-  // one slot per environment, so that every warp loads and stores whole 256-byte row segments together and the block
-  // scheduler overlaps the CTAs' load / compute / store phases; the work queue only pays off for long calls.
-  if (mode == 1 && k <= SHIPENV_STREAMING_K) persistent = 0;
+  // (A static grid -- one slot per environment -- for launches of a few _step() was measured and is not the default:
+  //  one step per launch reaches 0.42 / 0.79 of the HBM peak at 1e5 / 1e6 environments with the persistent grid, 0.39 /
+  //  0.68 with the static one.  SHIPENV_STREAMING_K=k selects it for launches of at most k steps.)
+  if (mode == 1 && k <= h->streaming_k) persistent = 0;
   if (h->time_kernels) {
     if (h->kernel_pending) {                 // fold the previous launch into the sum before reusing the events
       float ms = 0.f;
@@ -449,6 +450,7 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
   }
   *h->done_host = 0;
   if (const char* pm = getenv("SHIPENV_PERSISTENT")) h->persist_mode = atoi(pm);   // 1 (default), 0, -1 auto
+  if (const char* sk = getenv("SHIPENV_STREAMING_K")) h->streaming_k = atoi(sk);    // measurement aid
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return SHIPENV_OK;

@@ -211,6 +211,14 @@ def prepare_colav_env(args, iw=True, num_envs=1, device=None, init_states=None, 
     return env, assets
 
 
+def _machinery_state(ship_model) -> float:
+    """Initial value of the machinery state row: shaft speed (ShipModelAST), thrust force (thrust-state model), 0."""
+    mm = getattr(ship_model, "ship_machinery_model", None)
+    if mm is None:
+        return 0.0
+    return float(mm.omega) if hasattr(mm, "omega") else float(mm.thrust)
+
+
 def jittered_init_states(assets: List[ShipAssets], num_envs: int, pos_jitter_m: float = 100.0, seed: int = 1,
                          device="cuda"):
     """Per-environment initial states [7, 2 * num_envs]: the assets' configured initial values with a
@@ -223,7 +231,7 @@ def jittered_init_states(assets: List[ShipAssets], num_envs: int, pos_jitter_m: 
         sc = a.ship_model.simulation_config
         vals = [sc.initial_north_position_m, sc.initial_east_position_m, sc.initial_yaw_angle_rad,
                 sc.initial_forward_speed_m_per_s, sc.initial_sideways_speed_m_per_s, sc.initial_yaw_rate_rad_per_s,
-                a.ship_model.ship_machinery_model.omega if hasattr(a.ship_model, "ship_machinery_model") else 0.0]
+                _machinery_state(a.ship_model)]
         for i, v in enumerate(vals):
             base[i, :, role] = float(v)
     jit = (torch.rand((2, num_envs, 2), generator=g, dtype=torch.float64) * 2.0 - 1.0) * pos_jitter_m

@@ -264,6 +264,19 @@ def simplified_rollout(cfg: ShipConfig, thrust_time_constant: float, initial_thr
     return out, wpt, st
 
 
+def set_simplified(thrust_time_constant=None, initial_thrust: float = 0.0):
+    """Machinery constants of the thrust-state model (A8') for OracleEnv runs whose ships are MODEL_SIMPLIFIED;
+    None switches it off.  Global in the C library: set it before constructing the OracleEnv."""
+    L = lib()
+    L.orc_set_simplified.argtypes = [C.POINTER(SimplifiedMachinery)]
+    L.orc_set_simplified.restype = None
+    if thrust_time_constant is None:
+        L.orc_set_simplified(None)
+    else:
+        m = SimplifiedMachinery(float(thrust_time_constant), float(initial_thrust))
+        L.orc_set_simplified(C.byref(m))
+
+
 def bench_episodes(cfg: EnvConfig, actions: np.ndarray, jitter_ne=None, n_threads: int = 0):
     """n_envs x n_rl_steps float64 actions -> (total _step() count, returns[n_envs], events[n_envs])."""
     actions = np.ascontiguousarray(actions, dtype=np.float64)
@@ -299,6 +312,17 @@ def ship_config_from_asset(asset, post_reset: bool = False) -> ShipConfig:
     f.update(radius_of_acceptance=nav.ra, lookahead_distance=nav.r, integral_gain=nav.ki,
              integrator_windup_limit=nav.integrator_limit, desired_forward_speed=asset.desired_forward_speed)
     route = np.stack([np.asarray(nav.north, dtype=np.float64), np.asarray(nav.east, dtype=np.float64)], axis=1)
+    if hasattr(sm, "ship_machinery_model") and hasattr(sm.ship_machinery_model, "thrust_time_constant"):
+        # hull + SimplifiedMachineryModel (A8'): the machinery state slot holds the thrust force; the time constant
+        # goes through set_simplified()
+        mm = sm.ship_machinery_model
+        tc = asset.throttle_controller
+        f.update(rudder_angle_to_sway_force_coefficient=mm.c_rudder_v, rudder_angle_to_yaw_force_coefficient=mm.c_rudder_r,
+                 hotel_load=mm.hotel_load, main_engine_capacity=mm.mode.main_engine_capacity,
+                 electrical_capacity=mm.mode.electrical_capacity, initial_propeller_shaft_speed_rad_per_s=mm.thrust,
+                 dt_shaft=mm.int.dt, kp_ship_speed=tc.ship_speed_controller.kp, ki_ship_speed=tc.ship_speed_controller.ki)
+        return make_ship_config(route, model_kind=MODEL_SIMPLIFIED,
+                                shaft_generator_state=mm.mode.shaft_generator_state, **f)
     if hasattr(sm, "ship_machinery_model"):
         mm = sm.ship_machinery_model
         tc = asset.throttle_controller

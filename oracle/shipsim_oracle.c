@@ -172,7 +172,16 @@ static double speed_command(const OrcShipConfig* c, OrcShipState* s, double set_
 /* update_differentials + integrate_differentials + int.next_time:
  * SimpleShipModel ship_model.py:351-416; ShipModelAST rl_env ship_model.py:834-901;
  * ShipMachineryModel ship_engine.py:403-443; EulerInt utils.py:42-53. */
-static const OrcSimplifiedMachinery* g_simplified = NULL;   /* set by orc_simplified_rollout only */
+static const OrcSimplifiedMachinery* g_simplified = NULL;   /* set by orc_simplified_rollout / orc_set_simplified */
+static OrcSimplifiedMachinery g_simplified_env;              /* copy made by orc_set_simplified */
+
+/* env-level runs of the thrust-state model (A8'): the machinery constants the ship configuration struct does not
+ * hold, for every ORC_MODEL_SIMPLIFIED ship stepped afterwards (not re-entrant; NULL switches it off).  The initial
+ * thrust force is the ship's initial_propeller_shaft_speed_rad_per_s field (the machinery state's slot). */
+void orc_set_simplified(const OrcSimplifiedMachinery* m) {
+  if (m) { g_simplified_env = *m; g_simplified = &g_simplified_env; }
+  else g_simplified = NULL;
+}
 
 static void ship_dynamics(const OrcShipConfig* c, const Derived* d, OrcShipState* s, double command,
                           double rudder_angle) {
@@ -268,9 +277,10 @@ static void log_row(OrcShipState* s) {
 void orc_simplified_rollout(const OrcShipConfig* c, const OrcSimplifiedMachinery* m, OrcShipState* s, int64_t n_steps,
                             int record_every, double* out_states, int32_t* out_wpt) {
   /* bare loop of a hull driven by SimplifiedMachineryModel (A8' of SURVEY.md section 8a); not re-entrant */
+  const OrcSimplifiedMachinery* saved = g_simplified;
   g_simplified = m;
   orc_ship_rollout(c, s, n_steps, record_every, out_states, out_wpt);
-  g_simplified = NULL;
+  g_simplified = saved;
 }
 
 void orc_ship_rollout(const OrcShipConfig* c, OrcShipState* s, int64_t n_steps, int record_every,

@@ -701,6 +701,67 @@ def test_trajectory_log_matches_reference_simulation_results(kind):
     env.close()
 
 
+def test_thrust_state_model_env_episodes_match_oracle():
+    """A8' at the env level: 64 jittered MultiShipRLEnv episodes whose hulls are driven by the SimplifiedMachineryModel
+    (thrust-force state T) and ThrottleFromSpeedSetPointSimplifiedPropulsion, each against its own oracle run -- flags
+    bit-exact, states 1e-9.  (The reference cannot run this model inside its env: SimplifiedMachineryModel has no
+    recorded initial state to reset() to and its throttle controller does not take the env's measured_shaft_speed
+    argument; its dynamics are pinned by the bare-loop golden bare_simplified_dt4_test.)"""
+    B = 64
+    tau, t0, kp, ki = 30.0, 0.0, 3.0, 0.02
+    args = S.get_env_args(time_step=4)
+    assets, m = S.build_simplified_assets(args, thrust_force_dynamic_time_constant=tau, initial_thrust_force=t0, kp=kp, ki=ki)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=100.0, seed=31)
+    env = S.MultiShipRLEnv(assets=assets, map=m, args=args, num_envs=B, init_states=init)
+    assert env._params.ship[0].model_kind == L.MODEL_SIMPLIFIED
+    gen = torch.Generator().manual_seed(32)
+    actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
+    O.set_simplified(tau, t0)
+    try:
+        base_cfg = O.env_config_from_assets(assets, env.map, env.args, O.ENV_RL)
+        init_np = init.cpu().numpy().reshape(7, B, 2)
+        oracles = []
+        for b in range(B):
+            cfg = O.EnvConfig()
+            C.memmove(C.byref(cfg), C.byref(base_cfg), C.sizeof(O.EnvConfig))
+            for role in range(2):
+                cfg.ship[role].initial_north_position_m = init_np[0, b, role]
+                cfg.ship[role].initial_east_position_m = init_np[1, b, role]
+            oe = O.OracleEnv(cfg)
+            oe.reset()
+            oracles.append(oe)
+        env.reset()
+        alive = np.ones(B, dtype=bool)
+        worst, seen = 0.0, 0
+        for j in range(9):
+            env.step(actions[:, j].cuda())
+            _sync()
+            info = env.info_buf.cpu().numpy(); nsub = env.nsub_buf.cpu().numpy(); rew = env.reward_buf.cpu().numpy()
+            st = env.ship_f64.cpu().numpy().reshape(L.SF_COUNT, B, 2)
+            states = np.stack([st[0], st[1], st[2], st[3], st[4], st[5], st[6], st[8]], axis=-1)
+            kk = env.next_wpt.cpu().numpy()
+            for b in range(B):
+                if not alive[b]:
+                    continue
+                r = oracles[b].step(float(actions[b, j]))
+                osh = oracles[b].st.ship
+                assert nsub[b] == r.n_substeps and (info[b] & L.INFO_EVENT_MASK) == r.events, (b, j)
+                assert bool(info[b] & L.INFO_DONE) == bool(r.done) and kk[b, 0] == osh[0].next_wpt and kk[b, 1] == osh[1].next_wpt
+                err = max(rel_err(states[b, role], oracle_ship_vec(osh[role]), np.array([1, 1, 1, 1, 1, 1e-3, 1e3, 1])).max()
+                          for role in range(2))
+                assert err < REL_TOL, (b, j, err)
+                assert rel_err(rew[b], r.reward, 1e-3) < 1e-7
+                worst = max(worst, err)
+                seen |= r.events
+                if r.done:
+                    alive[b] = False
+        assert not alive.any() and seen != 0
+        print(f"[thrust-state model, env level] worst rel err {worst:.2e}")
+    finally:
+        O.set_simplified(None)
+    env.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # NonIW env (config 1) batched: _step() in chunks against per-environment oracle runs
 # ------------------------------------------------------------------------------------------------
