@@ -382,6 +382,22 @@ bool host_locked(shipenv* h, const void* ptr, size_t bytes) {
 int fetch_outputs(shipenv* h, float* obs_host, double* reward_host, int32_t* info_host, int32_t* nsub_host) {
   const size_t B = (size_t)h->num_envs;
   Pinned pv = pinned_view(h);
+  // One DMA instead of four when the outputs lie back to back (obs | reward | info | nsub) on both sides -- the layout
+  // ast_sac_b200.env allocates: a D2H copy of 48 B per environment is bandwidth-bound, four small ones are
+  // latency-bound as well.
+  {
+    const char* d0 = reinterpret_cast<const char*>(h->buf.obs_f32);
+    char* h0 = reinterpret_cast<char*>(obs_host);
+    const bool packed_dev = (const char*)h->buf.reward == d0 + B * 32 && (const char*)h->buf.info_i32 == d0 + B * 40 &&
+                            (const char*)h->buf.nsub_i32 == d0 + B * 44;
+    const bool packed_host = obs_host && (char*)reward_host == h0 + B * 32 && (char*)info_host == h0 + B * 40 &&
+                             (char*)nsub_host == h0 + B * 44;
+    if (packed_dev && packed_host && host_locked(h, obs_host, B * 48)) {
+      CUDA_TRY(cudaMemcpyAsync(obs_host, h->buf.obs_f32, B * 48, cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      return SHIPENV_OK;
+    }
+  }
   const bool d_obs = obs_host && host_locked(h, obs_host, B * 32);
   const bool d_rew = reward_host && host_locked(h, reward_host, B * 8);
   const bool d_info = info_host && host_locked(h, info_host, B * 4);

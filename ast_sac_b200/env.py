@@ -348,10 +348,13 @@ class BatchedShipEnv:
         self.env_i32 = torch.zeros((L.EI_COUNT, B), dtype=i32, device=dev)
         self.iw_f64 = torch.zeros((2, L.MAX_IW, B), dtype=f64, device=dev)
         self.prev_f32 = torch.zeros((4, B), dtype=f32, device=dev)
-        self.obs_buf = torch.zeros((B, 8), dtype=f32, device=dev)
-        self.reward_buf = torch.zeros((B,), dtype=f64, device=dev)
-        self.info_buf = torch.zeros((B,), dtype=i32, device=dev)
-        self.nsub_buf = torch.zeros((B,), dtype=i32, device=dev)
+        # the four per-call outputs back to back (obs | reward | info | nsub, 48 B per environment): the host-buffer
+        # path then fetches them with one copy
+        self._out_all = torch.zeros((48 * B,), dtype=torch.uint8, device=dev)
+        self.obs_buf = self._out_all[:32 * B].view(f32).view(B, 8)
+        self.reward_buf = self._out_all[32 * B:40 * B].view(f64)
+        self.info_buf = self._out_all[40 * B:44 * B].view(i32)
+        self.nsub_buf = self._out_all[44 * B:48 * B].view(i32)
         self.counters = torch.zeros((4,), dtype=torch.int64, device=dev)
         assert self.ship_f64.numel() == lay.ship_f64 and self.iw_f64.numel() == lay.iw_f64
         assert self.env_f64.numel() == lay.env_f64 and self.env_i32.numel() == lay.env_i32
@@ -374,6 +377,7 @@ class BatchedShipEnv:
             L.load().shipenv_destroy(self._handle)      # (releases the host registrations of _host_arrays)
             self._handle = None
             self.__dict__.pop("_host_bufs", None)
+            self.__dict__.pop("_host_actions", None)
 
     def __del__(self):
         try:
@@ -385,7 +389,8 @@ class BatchedShipEnv:
     def __getstate__(self):
         d = {k: v for k, v in self.__dict__.items() if k not in (
             "_handle", "_params", "ship_f64", "ship_i32", "env_f64", "env_i32", "iw_f64", "prev_f32", "obs_buf",
-            "reward_buf", "info_buf", "nsub_buf", "counters", "log_f64", "log_count", "_log_envs", "_host_bufs")}
+            "reward_buf", "info_buf", "nsub_buf", "_out_all", "counters", "log_f64", "log_count", "_log_envs", "_host_bufs",
+            "_host_actions")}
         d["_device"] = str(self._device)
         return d
 
@@ -614,18 +619,38 @@ class BatchedShipEnv:
 
     # -- host-buffer path (numpy in / numpy out through the C ABI's *_host entry points) -----------
     def _host_arrays(self):
-        """The env's own host arrays of the host-buffer path, page-locked once through shipenv_register_host (the env
-        owns them for its whole life, so the registration cannot outlive the memory; close() releases them)."""
+        """The env's own host arrays of the host-buffer path: the four outputs back to back in one page-locked block
+        (mirrors the device layout, so one copy fetches them) and an actions array.  Registered once through
+        shipenv_register_host -- the env owns them for its whole life, so the registration cannot outlive the memory;
+        close() releases them."""
         if not hasattr(self, "_host_bufs"):
             B = self.num_envs
-            bufs = dict(actions=np.empty(B, np.float64), obs=np.empty((B, 8), np.float32), reward=np.empty(B, np.float64),
-                        info=np.empty(B, np.int32), nsub=np.empty(B, np.int32))
+            block = np.empty(48 * B, np.uint8)
+            bufs = dict(actions=np.empty(B, np.float64), block=block,
+                        obs=block[:32 * B].view(np.float32).reshape(B, 8), reward=block[32 * B:40 * B].view(np.float64),
+                        info=block[40 * B:44 * B].view(np.int32), nsub=block[44 * B:48 * B].view(np.int32))
             lib = L.load()
-            for a in bufs.values():
+            for key in ("actions", "block"):
+                a = bufs[key]
                 if a.nbytes >= (16 << 10):          # small buffers: staging is as fast as a direct copy
                     L.check(lib.shipenv_register_host(self._handle, a.ctypes.data, a.nbytes))
             self._host_bufs = bufs
         return self._host_bufs
+
+    def register_host_actions(self, actions: np.ndarray):
+        """Page-lock a caller-owned float64 array of action rows (shape [..., num_envs]) that will be passed to
+        step_host() row by row and that outlives this env's use of it: step_host() then copies straight from the
+        row instead of staging it.  Call unregister_host_actions() before the array is freed or reallocated."""
+        a = np.ascontiguousarray(actions)
+        if a is not actions or a.dtype != np.float64:
+            raise ValueError("actions must be a C-contiguous float64 array")
+        L.check(L.load().shipenv_register_host(self._handle, a.ctypes.data, a.nbytes))
+        self._host_actions = (a.ctypes.data, a.nbytes, a)
+
+    def unregister_host_actions(self):
+        if getattr(self, "_host_actions", None) is not None:
+            L.check(L.load().shipenv_unregister_host(self._handle, self._host_actions[0]))
+            self._host_actions = None
 
     def step_host(self, actions: np.ndarray):
         """step(action) through host buffers: numpy actions in, numpy (obs, reward, info word, substeps) out.  The
@@ -635,8 +660,13 @@ class BatchedShipEnv:
         a = np.asarray(actions, dtype=np.float64).reshape(-1)
         if a.size != B:
             raise ValueError(f"expected {B} actions")
-        np.copyto(hb["actions"], a)      # one persistent page-locked array instead of whatever the caller passed
-        L.check(L.load().shipenv_step_host(self._handle, hb["actions"].ctypes.data, hb["obs"].ctypes.data,
+        reg = getattr(self, "_host_actions", None)
+        if reg is not None and a.flags.c_contiguous and reg[0] <= a.ctypes.data and a.ctypes.data + a.nbytes <= reg[0] + reg[1]:
+            src = a                          # a row of the array the caller registered: no staging copy
+        else:
+            np.copyto(hb["actions"], a)      # one persistent page-locked array instead of whatever the caller passed
+            src = hb["actions"]
+        L.check(L.load().shipenv_step_host(self._handle, src.ctypes.data, hb["obs"].ctypes.data,
                                            hb["reward"].ctypes.data, hb["info"].ctypes.data, hb["nsub"].ctypes.data))
         return hb["obs"], hb["reward"], hb["info"], hb["nsub"]
 

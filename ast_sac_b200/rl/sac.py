@@ -189,22 +189,47 @@ class SACTrainer:
     # update above.  The five MLPs are tiny (9 -> 256 -> 256 -> 1, batch 256), so an eager update is ~100 kernel
     # launches of a few microseconds each; replaying them as one graph removes the launch overhead.
     def capture(self, replay_buffer, batch_size, warmup=3):
+        """Capture one update (batch sampling included) as a CUDA graph.  The `warmup` eager updates torch needs
+        before a capture run on live replay data, so the networks, the optimizer states and the update counter are
+        snapshotted before them and restored IN PLACE afterwards (the graph holds the tensors' addresses): the graphed
+        run performs exactly the updates the caller asks for with train_graphed() -- the same schedule as the eager
+        trainer and the reference, none extra."""
         if self.target_update_period != 1:
             raise ValueError("graph capture assumes target_update_period == 1 (the reference default)")
         if not self.policy_optimizer.defaults.get("capturable", False):
             raise ValueError("construct the trainer with capturable=True to capture its optimizers")
         dev = next(self.policy.parameters()).device
+        optimizers = [self.policy_optimizer, self.qf1_optimizer, self.qf2_optimizer]
+        params = [p for net in self.networks for p in net.parameters()] + [b for net in self.networks for b in net.buffers()]
+        if self.use_automatic_entropy_tuning:
+            optimizers.append(self.alpha_optimizer)
+            params.append(self.log_alpha)
+        saved_params = [p.detach().clone() for p in params]
+        saved_state = {id(t): t.detach().clone() for opt in optimizers for st in opt.state.values()
+                       for t in st.values() if torch.is_tensor(t)}
+        steps_before = self._n_train_steps_total
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):
                 self.train_from_torch(replay_buffer.random_batch(batch_size))
         torch.cuda.current_stream(dev).wait_stream(side)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self.train_from_torch(replay_buffer.random_batch(batch_size))
+        with torch.no_grad():
+            for p, q in zip(params, saved_params):
+                p.copy_(q)
+            for opt in optimizers:
+                for st in opt.state.values():
+                    for t in st.values():
+                        if torch.is_tensor(t):
+                            if id(t) in saved_state:
+                                t.copy_(saved_state[id(t)])
+                            else:
+                                t.zero_()           # created by the warm-up: a fresh Adam state (step 0, zero moments)
         self._graph = graph
-        self._n_train_steps_total -= 1          # the capture pass itself does not run the kernels
+        self._n_train_steps_total = steps_before
         return graph
 
     def train_graphed(self):

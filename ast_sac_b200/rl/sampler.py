@@ -73,6 +73,8 @@ def batched_ast_sac_rollout(env, agent, max_path_length: int, replay_buffer=None
         env.set_done(~alive)                       # environments this wave does not need are parked, not simulated
     O, A, R, NO, T, D, V, E = [], [], [], [], [], [], [], []
     for _ in range(int(max_path_length)):
+        if O and not bool(alive.any()):            # every active environment is done: no full-width steps for nobody
+            break
         a = agent.get_actions(obs, deterministic=deterministic) if deterministic else agent.get_actions(obs)
         next_obs, r, done, info = env.step(a)
         next_obs = next_obs.clone()
@@ -92,7 +94,13 @@ def batched_ast_sac_rollout(env, agent, max_path_length: int, replay_buffer=None
 class VectorizedPathCollector:
     """MdpPathCollector for the batched env.  ``collect_new_steps`` runs whole-batch episodes until at
     least ``num_steps`` transitions were collected (the last wave only activates as many environments
-    as are still needed, so the overshoot is below one episode per environment)."""
+    as are still needed, so the overshoot is below one episode per environment).
+
+    Differences from the reference's collector (path_collector.py:36-75), which steps one environment at a time:
+    every path runs to its end -- the last one is not truncated to the remaining step budget
+    (``max_path_length_this_loop``) and ``discard_incomplete_paths`` has nothing to discard -- so a loop can add up
+    to one episode more than ``num_steps`` transitions to the replay buffer; and the transitions of a wave enter the
+    buffer time-interleaved (step t of every environment, then step t + 1), not path after path."""
 
     def __init__(self, env, policy, replay_buffer=None, max_num_epoch_paths_saved=None, deterministic=False,
                  save_env_in_snapshot=False):
