@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AST_SAC_B200_LIB") or os.path.join(_HERE, "csrc", "libshipenv.so")
 
 MAX_WP, MAX_IW, MAX_POLY, MAX_VERT = 32, 30, 16, 128
-ABI_VERSION = 8
+ABI_VERSION = 9
 MATH_STRICT, MATH_FAST = 0, 1
 MODEL_SIMPLE, MODEL_DETAILED, MODEL_SIMPLIFIED = 0, 1, 2
 ENV_COLAV_NONIW, ENV_COLAV_IW, ENV_RL = 0, 1, 2
@@ -60,7 +60,7 @@ class Params(C.Structure):
                 ("cos_omega", _D), ("sin_omega", _D), ("n_base0", _D), ("e_base0", _D), ("roa", _D),
                 ("poly_start", C.c_int32 * (MAX_POLY + 1)), ("n_poly", C.c_int32), ("env_kind", C.c_int32),
                 ("collav", C.c_int32), ("max_sampling_frequency", C.c_int32), ("abi_version", C.c_int32),
-                ("math_mode", C.c_int32)]
+                ("math_mode", C.c_int32), ("obs_sampled_route", C.c_int32)]
 
 
 class Buffers(C.Structure):
@@ -139,9 +139,9 @@ def measure_fp64_peak(device: int = 0, repeats: int = 5) -> float:
 
 
 def selftest_math(device: int = 0, n: int = 1 << 24, seed: int = 1):
-    """(sincos, atan, sqrt, division, exp, atan2, fmod) bitwise mismatch counts of csrc/shipenv_math.cuh vs the CUDA
-    math library: fast build, then strict build (14 numbers, all expected 0)."""
-    out = (C.c_ulonglong * 14)()
+    """(sincos, atan, sqrt, division, exp, atan2, fmod, x*rsqrt(x) beyond 2 ulp, a*rsqrt(x) beyond 2 ulp) mismatch counts
+    of csrc/shipenv_math.cuh vs the CUDA math library: fast build, then strict build (18 numbers, all expected 0)."""
+    out = (C.c_ulonglong * 18)()
     check(load().shipenv_selftest_math(device, n, seed, out))
     return list(out)
 

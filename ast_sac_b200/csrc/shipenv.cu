@@ -109,16 +109,20 @@ int validate(const ShipEnvParams* p, long long num_envs) {
       return fail(SHIPENV_E_ARG, "ship[%d].thrust_tau must be positive", s);
     if (q.n_wp < 2 || q.n_wp > SHIPENV_MAX_WP) return fail(SHIPENV_E_ARG, "ship[%d].n_wp must be in [2, %d]", s, SHIPENV_MAX_WP);
     if (!(q.dt > 0.0) || !(q.ctrl_dt > 0.0)) return fail(SHIPENV_E_ARG, "ship[%d] time steps must be positive", s);
+    // the fast build forms e_ct / sqrt(R^2 - e_ct^2) without the reference's clamp of the root to >= 1e-6
+    // (LOS_guidance.py:113-115), which cannot bind for R > 1e-5 m: the root is >= 0.141 R
+    if (p->math_mode == SHIPENV_MATH_FAST && !(q.los_r > 1e-5))
+      return fail(SHIPENV_E_ARG, "ship[%d].los_r (lookahead distance) must exceed 1e-5 m in the fast build", s);
     if (q.model_kind != SHIPENV_MODEL_SIMPLE && !(q.dt_shaft > 0.0))
       return fail(SHIPENV_E_ARG, "ship[%d].dt_shaft must be positive", s);
   }
-  if (p->env_kind != SHIPENV_ENV_COLAV_NONIW && p->ship[1].n_wp + p->max_sampling_frequency > 255)
+  if ((p->env_kind != SHIPENV_ENV_COLAV_NONIW || p->obs_sampled_route) && p->ship[1].n_wp + p->max_sampling_frequency > 255)
     return fail(SHIPENV_E_ARG, "route too long");
   return SHIPENV_OK;
 }
 
 SenvView view(const shipenv* h) {
-  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav,
+  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav, h->sm_count,
                   h->log_dev, h->log_count_dev, h->log_envs, h->log_capacity};
 }
 
@@ -631,8 +635,9 @@ int shipenv_init_step(shipenv_t* h, void* stream) {
 int shipenv_step(shipenv_t* h, const double* actions_dev, void* stream) {
   int rc = check_ready(h, true);
   if (rc) return rc;
-  if (h->params.env_kind == SHIPENV_ENV_COLAV_NONIW)
-    return fail(SHIPENV_E_STATE, "step(action) needs an intermediate-waypoint env kind (COLAV_IW or RL)");
+  if (h->params.env_kind == SHIPENV_ENV_COLAV_NONIW && !h->params.obs_sampled_route)
+    return fail(SHIPENV_E_STATE, "step(action) on the NonIW env kind needs params.obs_sampled_route (an obstacle ship "
+                                 "with a HeadingBySampledRouteController)");
   if (!actions_dev) return fail(SHIPENV_E_ARG, "actions_dev is NULL");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -814,11 +819,11 @@ int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long lo
     return fail(SHIPENV_E_CUDA, "no such CUDA device %d", device);
   CUDA_TRY(cudaSetDevice(device));
   unsigned long long* dev = nullptr;
-  CUDA_TRY(cudaMalloc(&dev, 14 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemset(dev, 0, 14 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&dev, 18 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(dev, 0, 18 * sizeof(unsigned long long)));
   CUDA_TRY(senv_fast::launch_math_selftest(n, seed, dev, nullptr));
-  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 7, nullptr));
-  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 14 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CUDA_TRY(senv_strict::launch_math_selftest(n, seed, dev + 9, nullptr));
+  CUDA_TRY(cudaMemcpy(mismatches_host, dev, 18 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   cudaFree(dev);
   return SHIPENV_OK;
 }

@@ -41,6 +41,16 @@
 #ifndef SENV_ENV_BLOCK
 #define SENV_ENV_BLOCK 128  // threads per CTA of the env kernel
 #endif
+#ifndef SENV_VMAG_RSQRT
+#define SENV_VMAG_RSQRT 1   // fast build: relative wind speed as x * rsqrt(x), within 2 ulp (3 links fewer: +0.6 %)
+#endif
+#ifndef SENV_SEG_SMEM
+#define SENV_SEG_SMEM 0     // LOS segment cache in shared memory instead of 14 registers (measured: colav_iw +0.9 %,
+                            // rl -2 %, one step per launch +4 %; profiles/r02_ncu_summary.md part 5)
+#endif
+#ifndef SENV_LOS_RSQRT
+#define SENV_LOS_RSQRT 1    // fast build: e_ct / sqrt(R^2 - e_ct^2) as e_ct * rsqrt(.) (11 dependent FP64 links fewer: +5 %)
+#endif
 
 namespace SENV_NS {
 
@@ -57,12 +67,49 @@ enum Mode { MODE_STEP = 0, MODE_SUBSTEPS = 1 };
 // ------------------------------------------------------------------------------------------------
 // registers of one ship
 // ------------------------------------------------------------------------------------------------
+// Current LOS segment (wp[k-1] -> wp[k]) and its bearing: seven doubles that change only at a waypoint switch.
+// SENV_SEG_SMEM = 1 keeps them in a per-lane shared-memory slot ([field][thread], conflict-free) instead of fourteen
+// registers: the simulator step re-reads them (LDS, off the dependent chains) and the registers go to the overlap
+// of the step's two long FP64 chains, which ptxas otherwise serialises at 128 registers per thread.
+#if SENV_SEG_SMEM
+constexpr int kSegStride = 128;     // threads per CTA of every kernel that holds a Ship
+struct Seg {
+  double* slot;
+  __device__ __forceinline__ double& pn() const { return slot[0]; }
+  __device__ __forceinline__ double& pe() const { return slot[kSegStride]; }
+  __device__ __forceinline__ double& sin_a() const { return slot[2 * kSegStride]; }
+  __device__ __forceinline__ double& cos_a() const { return slot[3 * kSegStride]; }
+  __device__ __forceinline__ double& wn() const { return slot[4 * kSegStride]; }
+  __device__ __forceinline__ double& we() const { return slot[5 * kSegStride]; }
+  __device__ __forceinline__ double& alpha() const { return slot[6 * kSegStride]; }
+};
+#define SENV_SEG_SLOT(ship) __shared__ double seg_slots_[7][kSegStride]; (ship).seg.slot = &seg_slots_[0][threadIdx.x]
+#else
+struct Seg {
+  double pn_, pe_, wn_, we_, alpha_, sin_a_, cos_a_;
+  __device__ __forceinline__ double& pn() { return pn_; }
+  __device__ __forceinline__ double& pe() { return pe_; }
+  __device__ __forceinline__ double& sin_a() { return sin_a_; }
+  __device__ __forceinline__ double& cos_a() { return cos_a_; }
+  __device__ __forceinline__ double& wn() { return wn_; }
+  __device__ __forceinline__ double& we() { return we_; }
+  __device__ __forceinline__ double& alpha() { return alpha_; }
+  __device__ __forceinline__ const double& pn() const { return pn_; }
+  __device__ __forceinline__ const double& pe() const { return pe_; }
+  __device__ __forceinline__ const double& sin_a() const { return sin_a_; }
+  __device__ __forceinline__ const double& cos_a() const { return cos_a_; }
+  __device__ __forceinline__ const double& wn() const { return wn_; }
+  __device__ __forceinline__ const double& we() const { return we_; }
+  __device__ __forceinline__ const double& alpha() const { return alpha_; }
+};
+#define SENV_SEG_SLOT(ship) ((void)0)
+#endif
+
 struct Ship {
   double north, east, yaw, u, v, r, omega, time;
   double e_ct, e_ct_int;
   double hdg_err_i, hdg_prev_err, spd_err_i, spd_aux;
-  // current LOS segment (wp[k-1] -> wp[k]) and its bearing
-  double pn, pe, wn, we, alpha, sin_a, cos_a;
+  Seg seg;
   int k;          // next waypoint index
   int n_wp;       // route length (file waypoints + sampled intermediate waypoints)
   int stop;
@@ -91,8 +138,8 @@ __device__ __forceinline__ void route_wp(const Route& rt, int n_iw, int idx, dou
 
 // end points of the current segment (the bearing and its sin / cos come from the cache rows of ship_f64)
 __device__ __forceinline__ void load_segment_points(const Route& rt, int n_iw, Ship& s) {
-  route_wp(rt, n_iw, s.k - 1, s.pn, s.pe);
-  route_wp(rt, n_iw, s.k, s.wn, s.we);
+  route_wp(rt, n_iw, s.k - 1, s.seg.pn(), s.seg.pe());
+  route_wp(rt, n_iw, s.k, s.seg.wn(), s.seg.we());
 }
 
 // bearing of a segment and its sin / cos (LOS_guidance.py:105-107).  (Moving this and the polygon edge loops out
@@ -112,15 +159,15 @@ __device__ __forceinline__ void refresh_segment(const Route& rt, int n_iw, Ship&
   load_segment_points(rt, n_iw, s);
   const int head = rt.n_file - 1;
   if (n_iw == 0 || s.k < head) {
-    s.alpha = rt.seg_file[3 * s.k]; s.sin_a = rt.seg_file[3 * s.k + 1]; s.cos_a = rt.seg_file[3 * s.k + 2];
+    s.seg.alpha() = rt.seg_file[3 * s.k]; s.seg.sin_a() = rt.seg_file[3 * s.k + 1]; s.seg.cos_a() = rt.seg_file[3 * s.k + 2];
   } else if (s.k >= head + n_iw - 1 && rt.seg_env) {
     const int row = (s.k == head + n_iw) ? SHIPENV_EF_SEG_END_ALPHA : SHIPENV_EF_SEG_NEW_ALPHA;
-    s.alpha = rt.seg_env[(long long)row * rt.stride];
-    s.sin_a = rt.seg_env[(long long)(row + 1) * rt.stride];
-    s.cos_a = rt.seg_env[(long long)(row + 2) * rt.stride];
+    s.seg.alpha() = rt.seg_env[(long long)row * rt.stride];
+    s.seg.sin_a() = rt.seg_env[(long long)(row + 1) * rt.stride];
+    s.seg.cos_a() = rt.seg_env[(long long)(row + 2) * rt.stride];
   } else {                                                   // an older sampled segment: not tabulated
-    const double3 b = segment_bearing(s.wn - s.pn, s.we - s.pe);
-    s.alpha = b.x; s.sin_a = b.y; s.cos_a = b.z;
+    const double3 b = segment_bearing(s.seg.wn() - s.seg.pn(), s.seg.we() - s.seg.pe());
+    s.seg.alpha() = b.x; s.seg.sin_a() = b.y; s.seg.cos_a() = b.z;
   }
 }
 
@@ -163,16 +210,25 @@ __device__ __forceinline__ const Derived& derived_of(const ShipEnvShipParams& P)
 // e_ct and the LOS integrator, returns the heading reference.
 __device__ __forceinline__ double los_guidance(const ShipEnvShipParams& P, Ship& s) {
   const Derived& D = derived_of(P);
-  double e_ct = -(s.north - s.pn) * s.sin_a + (s.east - s.pe) * s.cos_a;
+  double e_ct = -(s.north - s.seg.pn()) * s.seg.sin_a() + (s.east - s.seg.pe()) * s.seg.cos_a();
   const double R2 = D.los_r2;
   if (e_ct * e_ct >= R2) e_ct = D.los_r99;
   s.e_ct = e_ct;
+#if SENV_LOS_RSQRT && defined(SENV_HAVE_OWN_SQRT_DIV)
+  // e_ct / sqrt(R^2 - e_ct^2) as e_ct * rsqrt(..): the seed and the first refinement of the root (5 dependent FP64
+  // links instead of the 16 of root + division).  The refined reciprocal root is within 0.5 ulp + 2^-60 of the
+  // exact one (the correction term is ~2^-21 of it), the product adds one rounding: the same 2^-52 relative error
+  // bound as the reference's correctly rounded root followed by its correctly rounded division.  R^2 - e_ct^2 >=
+  // 0.0199 R^2 here, so the reference's clamp of the root to >= 1e-6 cannot bind for R > 1e-5 (checked on the host).
+  const double q = e_ct * senv_rsqrt(R2 - e_ct * e_ct);
+#else
   double delta = SENV_SQRT(R2 - e_ct * e_ct);
   if (!(delta > 1e-6)) delta = 1e-6;
   const double q = SENV_DIV(e_ct, delta);
+#endif
   if (fabs(s.e_ct_int + q) <= D.los_limit) s.e_ct_int += q;
   const double chi_r = senv_atan(-q - s.e_ct_int * D.los_ki);
-  return s.alpha + chi_r;
+  return s.seg.alpha() + chi_r;
 }
 
 // heading_offset / speed_factor: SBMPC's course offset (already negated, "pos == clockwise in sim",
@@ -184,7 +240,7 @@ struct NoStepHook { __device__ __forceinline__ void operator()(double, double) c
 
 // NavigationSystem.next_wpt (LOS_guidance.py:83-98): the waypoint switch at the top of the autopilot call.
 __device__ __forceinline__ bool wpt_reached(const Derived& H, const Ship& s) {
-  const double dn = s.wn - s.north, de = s.we - s.east;
+  const double dn = s.seg.wn() - s.north, de = s.seg.we() - s.east;
   return (dn * dn + de * de <= H.los_ra2) && (s.n_wp > s.k + 1);
 }
 
@@ -319,7 +375,11 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double sw = H.sin_wind_dir * cpsi - H.cos_wind_dir * spsi;
   const double u_rw = H.wind_speed * cw - u;
   const double v_rw = H.wind_speed * sw - v;
+#if SENV_VMAG_RSQRT && defined(SENV_HAVE_OWN_SQRT_DIV)
+  const double vmag = senv_sqrt_2ulp(u_rw * u_rw + v_rw * v_rw);
+#else
   const double vmag = SENV_SQRT(u_rw * u_rw + v_rw * v_rw);
+#endif
   const double tau_u = H.wind_cu * vmag * u_rw;
   const double tau_v = H.wind_cv * vmag * v_rw;
   const double tau_n = H.wind_cn * u_rw * v_rw;
@@ -962,9 +1022,9 @@ __device__ __forceinline__ void load_ship(const DevView& dv, long long n_ships, 
   s.hdg_prev_err = *p; p += n_ships;
   s.spd_err_i = *p; p += n_ships;
   s.spd_aux = *p; p += n_ships;
-  s.alpha = *p; p += n_ships;
-  s.sin_a = *p; p += n_ships;
-  s.cos_a = *p;
+  s.seg.alpha() = *p; p += n_ships;
+  s.seg.sin_a() = *p; p += n_ships;
+  s.seg.cos_a() = *p;
   const int packed = dv.buf.ship_i32[sidx];
   s.k = packed & 0xff;
   s.stop = (packed >> 8) & 1;
@@ -986,9 +1046,9 @@ __device__ __forceinline__ void store_ship(const DevView& dv, long long n_ships,
   *p = s.hdg_prev_err; p += n_ships;
   *p = s.spd_err_i; p += n_ships;
   *p = s.spd_aux; p += n_ships;
-  *p = s.alpha; p += n_ships;
-  *p = s.sin_a; p += n_ships;
-  *p = s.cos_a;
+  *p = s.seg.alpha(); p += n_ships;
+  *p = s.seg.sin_a(); p += n_ships;
+  *p = s.seg.cos_a();
   dv.buf.ship_i32[sidx] = (s.k & 0xff) | (s.stop << 8);
 }
 
@@ -1031,11 +1091,12 @@ k_reset(DevView dv, const uint8_t* __restrict__ mask, const double* __restrict__
   const int role = (int)(sidx & 1);
   if (mask && !mask[env]) return;
   const ShipEnvShipParams& P = sb.p.ship[role];
-  const bool dynamic_route = (role == 1) && (sb.p.env_kind != SHIPENV_ENV_COLAV_NONIW);
+  const bool dynamic_route = (role == 1) && (sb.p.env_kind != SHIPENV_ENV_COLAV_NONIW || sb.p.obs_sampled_route != 0);
   Route rt{P.wp_north, P.wp_east, dynamic_route ? dv.buf.iw_f64 + env : nullptr,
            dynamic_route ? dv.buf.iw_f64 + (long long)SHIPENV_MAX_IW * dv.num_envs + env : nullptr, dv.num_envs, P.n_wp,
            &sb.seg[role][0][0], dynamic_route ? dv.buf.env_f64 + env : nullptr};
   Ship s;
+  SENV_SEG_SLOT(s);
   int log_n = -1;
   if (reinit) {
     init_ship_regs(P, init_dev, n_ships, sidx, s);
@@ -1250,7 +1311,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   const long long n_slots = ((long long)gridDim.x * blockDim.x) >> 1;
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
-  const bool dynamic_route = IS_IW && role == 1;
+  // (the NonIW env samples intermediate waypoints too when it is driven with step(action), run_colav/env.py:678-800)
+  const bool dynamic_route = (IS_IW || G.obs_sampled_route != 0) && role == 1;
   const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
   const bool has_stop_branch = (role == 1) || !IS_RL;          // rl_env test_step has none (env.py:345-445)
   const bool collav_lane = SIMPLE && (role == 0 || !IS_IW);
@@ -1262,6 +1324,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
 
   // registers of the environment currently held by this lane
   Ship s = Ship{};
+  SENV_SEG_SLOT(s);
   s.k = 1;
   Route rt{P.wp_north, P.wp_east, nullptr, nullptr, B, P.n_wp, &sb.seg[role][0][0], nullptr};
   double travel_dist = 0.0, travel_time = 0.0, acc_reward = 0.0;
@@ -1509,7 +1572,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (role == 0 && s.time > derived_of(P).sim_time) my_flags |= 16;
       if (MODE == MODE_STEP && role == 1 && stage == 0) {
         // is_reach_radius_of_acceptance on the obstacle ship's next waypoint (check_condition.py:181-204)
-        const double rn = s.north - s.wn, re = s.east - s.we;
+        const double rn = s.north - s.seg.wn(), re = s.east - s.seg.we();
         if ((rn * rn + re * re) < sb.roa2) my_flags |= 32;
       }
       // bit 64: this ship's autopilot will switch to its next waypoint at the top of the next step
@@ -1760,6 +1823,7 @@ k_ship_rollout(DevView dv, int k_steps) {
   const ShipEnvShipParams& P = sb.p.ship[role];
   const Route rt{P.wp_north, P.wp_east, nullptr, nullptr, dv.num_envs, P.n_wp, &sb.seg[role][0][0], nullptr};
   Ship s;
+  SENV_SEG_SLOT(s);
   load_ship(dv, n_ships, sidx, s);
   s.n_wp = P.n_wp;
   load_segment_points(rt, 0, s);

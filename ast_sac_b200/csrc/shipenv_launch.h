@@ -30,6 +30,7 @@ struct SenvView {
   long long num_envs;
   SenvGrid grid;
   int collav;  // params->collav (selects the kernel instantiation)
+  int sm_count;  // multiprocessors of the device (the env kernel ranks its warps per SM, see k_env)
   // optional trajectory log (shipenv_set_trajectory_log)
   double* log_f64;
   int32_t* log_count;

@@ -258,6 +258,9 @@ def pack_params(assets, map_obj: PolygonObstacle, args, env_kind: int, post_rese
     else:
         raise ValueError(f"unknown collav_mode {collav!r}")
     P.max_sampling_frequency = msf
+    # MultiShipNonIWEnv.step(action) needs an obstacle ship whose autopilot can take intermediate waypoints
+    # (auto_pilot.update_route, run_colav/env.py:602: only HeadingBySampledRouteController has it)
+    P.obs_sampled_route = int(env_kind == L.ENV_COLAV_NONIW and isinstance(assets[1].auto_pilot, HeadingBySampledRouteController))
     P.abi_version = L.ABI_VERSION
     P.math_mode = math_mode
     return P
@@ -460,7 +463,8 @@ class BatchedShipEnv:
     def obs_route(self, env: int = 0):
         """Obstacle ship route of one environment, including the sampled intermediate waypoints."""
         nav = self.obs.auto_pilot.navigate
-        n_iw = int(self.env_i32[L.EI["sampling_count"], env]) if self.ENV_KIND != L.ENV_COLAV_NONIW else 0
+        sampled = self.ENV_KIND != L.ENV_COLAV_NONIW or self._params.obs_sampled_route
+        n_iw = int(self.env_i32[L.EI["sampling_count"], env]) if sampled else 0
         iw = self.iw_f64[:, :n_iw, env].cpu().numpy()
         north = [float(x) for x in nav.north[:-1]] + iw[0].tolist() + [float(nav.north[-1])]
         east = [float(x) for x in nav.east[:-1]] + iw[1].tolist() + [float(nav.east[-1])]
@@ -580,8 +584,9 @@ class BatchedShipEnv:
     def step(self, action):
         """env.step(action) (rl_env env.py:624-773): ``action`` holds un-normalised scoping angles [rad]
         (normalised to [-1, 1] when ``args.normalize_action``), one per environment."""
-        if self.ENV_KIND == L.ENV_COLAV_NONIW:
-            raise RuntimeError("MultiShipNonIWEnv is stepped with _step(); it takes no actions")
+        if self.ENV_KIND == L.ENV_COLAV_NONIW and not self._params.obs_sampled_route:
+            # run_colav/env.py:602: obs_ship_uses_scoping_angle() calls auto_pilot.update_route()
+            raise AttributeError("'HeadingByRouteController' object has no attribute 'update_route'")
         if getattr(self.args, "normalize_action", False) and action is not None:
             if isinstance(action, torch.Tensor):      # stay on the device: same affine map as env.py:192-196
                 lo = torch.as_tensor(self.action_space.low, device=action.device, dtype=action.dtype)

@@ -14,7 +14,7 @@ class BatchRLAlgorithm:
     def __init__(self, trainer, exploration_data_collector, evaluation_data_collector, replay_buffer, batch_size,
                  max_path_length, num_epochs, num_eval_steps_per_epoch, num_expl_steps_per_train_loop,
                  num_trains_per_train_loop, num_train_loops_per_epoch=1, min_num_steps_before_training=0, log=print,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, logger=None):
         self.trainer = trainer
         self.expl_data_collector, self.eval_data_collector = exploration_data_collector, evaluation_data_collector
         self.replay_buffer = replay_buffer
@@ -26,7 +26,47 @@ class BatchRLAlgorithm:
         self.min_num_steps_before_training = min_num_steps_before_training
         self.log = log
         self.use_cuda_graph = use_cuda_graph
+        # optional rl/logging.Logger: one progress.csv row and one snapshot per epoch, in the reference's format
+        self.logger = logger
+        self._t_start = time.perf_counter()
+        self._t_logging = 0.0         # duration of the previous epoch's logging (gtimer stamps it in the next epoch)
         self.history = []
+
+    def _get_snapshot(self):
+        """rl_algorithm.py:76-86."""
+        snapshot = {}
+        for k, v in self.trainer.get_snapshot().items():
+            snapshot['trainer/' + k] = v
+        for k, v in self.expl_data_collector.get_snapshot().items():
+            snapshot['exploration/' + k] = v
+        for k, v in self.eval_data_collector.get_snapshot().items():
+            snapshot['evaluation/' + k] = v
+        for k, v in self.replay_buffer.get_snapshot().items():
+            snapshot['replay_buffer/' + k] = v
+        return snapshot
+
+    def _log_stats(self, epoch, times):
+        """rl_algorithm.py:88-141: the same record_dict calls, prefixes and order; `times` holds this epoch's phase
+        durations under gtimer's stamp names."""
+        lg = self.logger
+        lg.log("Epoch {} finished".format(epoch), with_timestamp=True)
+        lg.record_dict({"epoch": epoch})
+        lg.record_dict(self.replay_buffer.get_diagnostics(), prefix='replay_buffer/')
+        lg.record_dict(self.trainer.get_diagnostics(), prefix='trainer/')
+        lg.record_dict(self.expl_data_collector.get_diagnostics(), prefix='expl/')
+        lg.record_dict(self.expl_data_collector.get_generic_path_information(), prefix='expl/')
+        lg.record_dict(self.eval_data_collector.get_diagnostics(), prefix='eval/')
+        lg.record_dict(self.eval_data_collector.get_generic_path_information(), prefix='eval/')
+        t = OrderedDict()
+        epoch_time = 0.0
+        for key in sorted(times):
+            epoch_time += times[key]
+            t['time/{} (s)'.format(key)] = times[key]
+        t['time/epoch (s)'] = epoch_time
+        t['time/total (s)'] = time.perf_counter() - self._t_start
+        lg.record_dict(t)
+        lg.record_tabular('Epoch', epoch)
+        lg.dump_tabular(with_prefix=False, with_timestamp=False)
 
     def _sync(self):
         if torch.cuda.is_available():
@@ -77,6 +117,16 @@ class BatchRLAlgorithm:
             times = OrderedDict()
             self.history.append(stats)
             self.log(stats)
+            if self.logger is not None:
+                ts = time.perf_counter()
+                self.logger.save_itr_params(epoch, self._get_snapshot())
+                t_save = time.perf_counter() - ts
+                # gtimer stamps of batch_rl_algorithm.py:47-106 ('data storing' is part of the rollout here: the
+                # transitions go straight into the GPU replay buffer; 'training' is the loop around the updates)
+                self._log_stats(epoch, {'evaluation sampling': t1 - t0, 'exploration sampling': t_expl,
+                                        'data storing': 0.0, 'sac training': t_train, 'training': 0.0,
+                                        'saving': t_save, 'logging': self._t_logging})
+                self._t_logging = time.perf_counter() - ts - t_save
             self.eval_data_collector.end_epoch(epoch)
             self.expl_data_collector.end_epoch(epoch)
         return self.history

@@ -70,14 +70,17 @@ class TanhGaussianPolicy(Mlp):
         log_std = torch.clamp(self.last_fc_log_std(h), LOG_SIG_MIN, LOG_SIG_MAX)
         return mean, torch.exp(log_std)
 
-    def rsample_and_logprob(self, obs):
+    def rsample_and_logprob(self, obs, return_dist=False):
         """TanhNormal.rsample_and_logprob (ast_sac/torch/core/distributions.py:318-447): a = tanh(z),
-        log pi = log N(z) - log(1 - a^2) in the numerically stable form."""
+        log pi = log N(z) - log(1 - a^2) in the numerically stable form.  ``return_dist`` also returns the
+        distribution's (normal_mean, normal_std) for the trainer's diagnostics."""
         mean, std = self(obs)
         z = mean + std * torch.randn_like(mean)
         a = torch.tanh(z)
         log_prob = -0.5 * ((z - mean) / std) ** 2 - torch.log(std) - 0.5 * math.log(2 * math.pi)
         log_prob = log_prob - 2.0 * (math.log(2.0) - z - F.softplus(-2.0 * z))
+        if return_dist:
+            return a, log_prob.sum(dim=1), mean, std
         return a, log_prob.sum(dim=1)
 
     @torch.no_grad()
@@ -138,7 +141,7 @@ class SACTrainer:
     def compute_loss(self, batch):
         rewards, terminals = batch['rewards'], batch['terminals']
         obs, actions, next_obs = batch['observations'], batch['actions'], batch['next_observations']
-        new_obs_actions, log_pi = self.policy.rsample_and_logprob(obs)
+        new_obs_actions, log_pi, pi_mean, pi_std = self.policy.rsample_and_logprob(obs, return_dist=True)
         log_pi = log_pi.unsqueeze(-1)
         if self.use_automatic_entropy_tuning:
             alpha_loss = -(self.log_alpha * (log_pi + self.target_entropy).detach()).mean()
@@ -158,6 +161,8 @@ class SACTrainer:
         q_target = torch.clamp(q_target, min=-self.clip_val, max=self.clip_val)
         qf1_loss = F.mse_loss(q1_pred, q_target.detach())
         qf2_loss = F.mse_loss(q2_pred, q_target.detach())
+        # what the reference's eval_statistics are made of (sac.py:262-292); kept as device tensors, read on demand
+        self._stat_tensors = (q2_pred, q_target, pi_mean, pi_std)
         return policy_loss, qf1_loss, qf2_loss, alpha_loss, alpha, log_pi, q1_pred
 
     def train_from_torch(self, batch):
@@ -181,7 +186,10 @@ class SACTrainer:
                 for src, dst in ((self.qf1, self.target_qf1), (self.qf2, self.target_qf2)):
                     for ps, pd in zip(src.parameters(), dst.parameters()):
                         pd.mul_(1.0 - self.soft_target_tau).add_(ps, alpha=self.soft_target_tau)
-        self._last = tuple(x.detach() if torch.is_tensor(x) else x for x in (policy_loss, qf1_loss, qf2_loss, alpha, log_pi, q1_pred))
+        q2_pred, q_target, mean, std = self._stat_tensors
+        self._last = tuple(x.detach() if torch.is_tensor(x) else x
+                           for x in (policy_loss, qf1_loss, qf2_loss, alpha, log_pi, q1_pred, q2_pred, q_target,
+                                     alpha_loss, mean, std))
 
     train = train_from_torch
 
@@ -239,10 +247,26 @@ class SACTrainer:
     def get_diagnostics(self):
         if not hasattr(self, "_last"):
             return OrderedDict()
-        policy_loss, qf1_loss, qf2_loss, alpha, log_pi, q1_pred = self._last
-        return OrderedDict([('QF1 Loss', float(qf1_loss)), ('QF2 Loss', float(qf2_loss)), ('Policy Loss', float(policy_loss)),
-                            ('Q1 Predictions Mean', float(q1_pred.mean())), ('Log Pis Mean', float(log_pi.mean())),
-                            ('Alpha', float(alpha))])
+        # the reference's key set and order (sac.py:262-292, torch_rl_algorithm.py:41-44), from the newest update
+        from .logging import create_stats_ordered_dict as stats
+        policy_loss, qf1_loss, qf2_loss, alpha, log_pi, q1_pred, q2_pred, q_target, alpha_loss, mean, std = self._last
+        d = OrderedDict([('num train calls', self._n_train_steps_total),
+                         ('QF1 Loss', float(qf1_loss)), ('QF2 Loss', float(qf2_loss)), ('Policy Loss', float(policy_loss))])
+        d.update(stats('Q1 Predictions', q1_pred))
+        d.update(stats('Q2 Predictions', q2_pred))
+        d.update(stats('Q Targets', q_target))
+        d.update(stats('Log Pis', log_pi))
+        d.update(stats('policy/mean', torch.tanh(mean)))      # TanhNormal.mean (distributions.py:425-427)
+        d.update(stats('policy/normal/std', std))
+        d.update(stats('policy/normal/log_std', torch.log(std)))
+        if self.use_automatic_entropy_tuning:
+            d['Alpha'] = float(alpha)
+            d['Alpha Loss'] = float(alpha_loss)
+        return d
+
+    def get_snapshot(self):
+        """sac.py:318-325."""
+        return dict(policy=self.policy, qf1=self.qf1, qf2=self.qf2, target_qf1=self.target_qf1, target_qf2=self.target_qf2)
 
     @property
     def networks(self):

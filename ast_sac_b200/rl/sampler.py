@@ -103,7 +103,7 @@ class VectorizedPathCollector:
     buffer time-interleaved (step t of every environment, then step t + 1), not path after path."""
 
     def __init__(self, env, policy, replay_buffer=None, max_num_epoch_paths_saved=None, deterministic=False,
-                 save_env_in_snapshot=False):
+                 save_env_in_snapshot=True):
         self._env, self._policy = env, policy
         self._replay_buffer = replay_buffer
         self._deterministic = deterministic
@@ -146,16 +146,30 @@ class VectorizedPathCollector:
         self._epoch_batches = deque(maxlen=self._epoch_batches.maxlen)
 
     def get_diagnostics(self):
+        """path_collector.py:83-94: totals and the path-length statistics of this epoch's paths."""
+        from .logging import create_stats_ordered_dict
         stats = OrderedDict([('num steps total', self._num_steps_total), ('num paths total', self._num_paths_total)])
         if self._epoch_batches:
-            lens = torch.cat([rb.path_lengths()[rb.valid[0]] for rb in self._epoch_batches]).float()
-            rets = torch.cat([rb.returns()[rb.valid[0]] for rb in self._epoch_batches]).float()
-            stats['path length Mean'] = float(lens.mean())
-            stats['path length Max'] = float(lens.max())
-            stats['path length Min'] = float(lens.min())
-            stats['Returns Mean'] = float(rets.mean())
-            stats['Returns Max'] = float(rets.max())
-            stats['Returns Min'] = float(rets.min())
+            lens = torch.cat([rb.path_lengths()[rb.valid[0]] for rb in self._epoch_batches])
+            stats.update(create_stats_ordered_dict('path length', lens))
+        return stats
+
+    def get_generic_path_information(self, stat_prefix=''):
+        """eval_util.get_generic_path_information (eval_util.py:12-66) over this epoch's paths, computed from the
+        batched rollouts on the device: Rewards / Returns / Actions statistics, 'Num Paths', 'Average Returns'.  (The
+        env_infos of these envs hold a string and three booleans, which that function skips as non-numeric.)"""
+        from .logging import create_stats_ordered_dict
+        stats = OrderedDict()
+        if not self._epoch_batches:
+            return stats
+        rew = torch.cat([rb.rewards.squeeze(-1)[rb.valid] for rb in self._epoch_batches])
+        act = torch.cat([rb.actions[rb.valid].reshape(-1) for rb in self._epoch_batches])
+        ret = torch.cat([rb.returns()[rb.valid[0]] for rb in self._epoch_batches])
+        stats.update(create_stats_ordered_dict('Rewards', rew, stat_prefix=stat_prefix))
+        stats.update(create_stats_ordered_dict('Returns', ret, stat_prefix=stat_prefix))
+        stats.update(create_stats_ordered_dict('Actions', act, stat_prefix=stat_prefix))
+        stats['Num Paths'] = int(ret.numel())
+        stats[stat_prefix + 'Average Returns'] = float(ret.to(torch.float64).mean())
         return stats
 
     def get_snapshot(self):

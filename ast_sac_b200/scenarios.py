@@ -137,8 +137,9 @@ def build_rl_assets(args, mode="PTI", test_init=None, obs_init=None, sim_time=10
     return [test, obs], PolygonObstacle(MAP_DATA)
 
 
-def build_colav_assets(args, iw=True, test_init=None, obs_init=None, sim_time=10000):
-    """run_colav/run_simplified_IW_model.py:55-211 (iw=True) / run_simplified_model.py:55-211 (iw=False)."""
+def build_colav_assets(args, iw=True, test_init=None, obs_init=None, sim_time=10000, obs_route=None):
+    """run_colav/run_simplified_IW_model.py:55-211 (iw=True) / run_simplified_model.py:55-211 (iw=False).
+    ``obs_route`` overrides the obstacle ship's route file (default: the script's own)."""
     ship_config, env_config = _ship_config(), _env_config()
     rudder_config = RudderConfiguration(rudder_angle_to_sway_force_coefficient=50e3,
                                         rudder_angle_to_yaw_force_coefficient=500e3, max_rudder_angle_degrees=30)
@@ -160,7 +161,7 @@ def build_colav_assets(args, iw=True, test_init=None, obs_init=None, sim_time=10
         speed_controller=ThrustFromSpeedSetPoint(gains=SpeedControllerGains(kp=.025, ki=700.5, kd=550.5),
                                                  max_thrust=np.inf, time_step=args.time_step),
         auto_pilot=HeadingBySampledRouteController(
-            get_data_path('obs_ship_route.txt' if iw else 'obs_ship_route_nonIW.txt'),
+            get_data_path(obs_route or ('obs_ship_route.txt' if iw else 'obs_ship_route_nonIW.txt')),
             heading_controller_gains=HeadingControllerGains(kp=.65, ki=0.001, kd=50),
             los_parameters=_los(args), time_step=args.time_step, max_rudder_angle=max_rudder, num_of_samplings=2),
         desired_forward_speed=4.0, integrator_term=[], time_list=[], stop_flag=False, type_tag='obs_ship')

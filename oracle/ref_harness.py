@@ -367,8 +367,8 @@ def make_colav_iw_env(args: Args, **kw):
     return MultiShipEnv(assets=assets, map=map_obj, args=args), assets
 
 
-def make_colav_noniw_env(args: Args, **kw):
-    assets, map_obj = build_colav_assets(args, obs_route="obs_ship_route_nonIW.txt", **kw)
+def make_colav_noniw_env(args: Args, obs_route="obs_ship_route_nonIW.txt", **kw):
+    assets, map_obj = build_colav_assets(args, obs_route=obs_route, **kw)
     from run_colav.env import MultiShipNonIWEnv
     return MultiShipNonIWEnv(assets=assets, map=map_obj, args=args), assets
 

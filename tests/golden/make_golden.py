@@ -100,12 +100,19 @@ def bare_rollout(kind: str, dt, who: int, n_steps: int, mode="PTI", post_reset=F
                 ctrl=ctrl[keep], next_wpt=wpt, dt_shaft=cfg.dt_shaft, meta=json.dumps(meta))
 
 
-def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None, obs_init=None, sim_time=10000):
-    """Episode of run_colav.MultiShipEnv ("colav") or rl_env MultiShipRLEnv ("rl"): KAT2 / KAT4."""
+def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None, obs_init=None, sim_time=10000,
+               obs_route="obs_ship_route.txt"):
+    """Episode of run_colav.MultiShipEnv ("colav"), rl_env MultiShipRLEnv ("rl"): KAT2 / KAT4, or of
+    run_colav.MultiShipNonIWEnv.step(action) ("noniw_step", run_colav/env.py:678-800: the NonIW class stepped with
+    scoping angles -- its obstacle ship must then carry a HeadingBySampledRouteController)."""
     args = H.Args(time_step=dt, collav_mode=collav)
     if kind == "colav":
         env, assets = H.make_colav_iw_env(args, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
         env_kind = O.ENV_COLAV_IW
+    elif kind == "noniw_step":
+        env, assets = H.make_colav_noniw_env(args, obs_route=obs_route, test_init=test_init, obs_init=obs_init,
+                                             sim_time=sim_time)
+        env_kind = O.ENV_COLAV_NONIW
     else:
         env, assets = H.make_rl_env(args, mode=mode, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
         env_kind = O.ENV_RL
@@ -113,6 +120,8 @@ def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None
     obs0 = env.reset()
     n = len(actions)
     meta = dict(kind=kind, dt=dt, collav=collav, mode=mode, test_init=test_init, obs_init=obs_init, sim_time=sim_time)
+    if kind == "noniw_step":
+        meta["obs_route"] = obs_route
     out = dict(meta=json.dumps(meta), cfg=struct_bytes(cfg), actions=np.asarray(actions, dtype=np.float64), obs0=np.asarray(obs0),
                obs=np.zeros((n, 8), np.float32), reward=np.zeros(n), done=np.zeros(n, np.int32),
                events=np.zeros(n, np.int32), terminal=np.zeros(n, np.int32), test_stop=np.zeros(n, np.int32),
@@ -122,12 +131,12 @@ def iw_episode(kind: str, dt, actions, collav="none", mode="PTI", test_init=None
                n_valid=0)
     for j, a in enumerate(actions):
         res = env.step(np.array([a], dtype=np.float64))
-        if kind == "colav":
+        if kind in ("colav", "noniw_step"):
             o, d, info = res
             r = 0.0
         else:
             o, r, d, info = res
-        out["obs"][j] = o
+        out["obs"][j, :len(o)] = o        # (six entries in the NonIW env)
         out["reward"][j] = r
         out["done"][j] = bool(d)
         out["events"][j] = events_bits(info['events'])
@@ -441,8 +450,31 @@ def main_sampler():
         print(name, len(out["actions"]), out["actions"].ravel(), out["events"][-1])
 
 
+def main_noniw_step():
+    """MultiShipNonIWEnv.step(action) (run_colav/env.py:678-800): the NonIW class driven with scoping angles.  Its
+    obs_step runs the collision avoidance for the obstacle ship too, has no travel tracker, and the observation has
+    six entries."""
+    deg = np.deg2rad
+    kat_actions = deg(np.array([-2, 0, 5, -5, 10, 0, 0, 0, 0], dtype=np.float64))
+    rng = np.random.default_rng(20261019)
+    save("colav_stepniw_dt4_kat", iw_episode("noniw_step", 4, kat_actions))
+    save("colav_stepniw_dt4_rand0", iw_episode("noniw_step", 4, rng.uniform(-np.pi / 6, np.pi / 6, size=9)))
+    save("colav_stepniw_dt4_fail", iw_episode("noniw_step", 4, deg(np.array([10., 30., 30., 30., 30., 30., 30., 30., 30.]))))
+    enc = np.array([0.02003677, -0.03365987, -0.01086403, -0.05174993, -0.0248715, -0.00825309, -0.04126783,
+                    0.01394448, -0.01252194])
+    save("colav_stepniw_dt4_collision", iw_episode("noniw_step", 4, enc))
+    save("colav_stepniw_dt4_sbmpc_encounter", iw_episode("noniw_step", 4, enc, collav="sbmpc"))
+    save("colav_stepniw_dt4_simple_collav", iw_episode("noniw_step", 4, kat_actions, collav="simple"))
+    save("colav_stepniw_dt4_timelimit", iw_episode("noniw_step", 4, kat_actions, sim_time=1000))
+    # the 11-waypoint file route of run_simplified_model.py: intermediate waypoints are inserted before its last point
+    save("colav_stepniw_dt4_longroute", iw_episode("noniw_step", 4, kat_actions * 0.5,
+                                                   obs_route="obs_ship_route_nonIW.txt"))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "sampler":
+    if len(sys.argv) > 1 and sys.argv[1] == "noniw_step":
+        main_noniw_step()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sampler":
         main_sampler()      # only the sampler fixtures (the others are unchanged)
     elif len(sys.argv) > 1 and sys.argv[1] == "logs":
         main_logs()
@@ -453,3 +485,4 @@ if __name__ == "__main__":
         main_sampler()
         main_logs()
         main_simplified()
+        main_noniw_step()

@@ -25,6 +25,10 @@ def env_from_meta(meta, num_envs=1, init_states=None, device=None, math_mode=Non
     if meta["kind"] == "noniw":
         return S.prepare_colav_env(args, iw=False, num_envs=num_envs, device=device, init_states=init_states,
                                    math_mode=math_mode, **kw)
+    if meta["kind"] == "noniw_step":         # MultiShipNonIWEnv driven with step(action)
+        return S.prepare_colav_env(args, iw=False, num_envs=num_envs, device=device, init_states=init_states,
+                                   sim_time=meta.get("sim_time", 10000), math_mode=math_mode,
+                                   obs_route=meta["obs_route"], **kw)
     raise ValueError(meta["kind"])
 
 
@@ -37,6 +41,8 @@ def assets_from_meta(meta):
         a, m = S.build_rl_assets(args, mode=meta.get("mode", "PTI"), sim_time=meta.get("sim_time", 10000), **kw)
     elif meta["kind"] == "colav":
         a, m = S.build_colav_assets(args, iw=True, sim_time=meta.get("sim_time", 10000), **kw)
+    elif meta["kind"] == "noniw_step":
+        a, m = S.build_colav_assets(args, iw=False, sim_time=meta.get("sim_time", 10000), obs_route=meta["obs_route"], **kw)
     else:
         a, m = S.build_colav_assets(args, iw=False, **kw)
     return a, m, args

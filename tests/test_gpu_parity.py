@@ -38,14 +38,14 @@ def test_device_math_equals_cuda_math_library_bit_for_bit():
     arguments, two seeds)."""
     for n, seed in ((1 << 24, 1), (1 << 22, 12345)):
         counts = L.selftest_math(0, n, seed)
-        assert counts == [0] * 14, f"sincos/atan/sqrt/div/exp/atan2/fmod mismatches (fast, strict) = {counts}"
+        assert counts == [0] * 18, f"sincos/atan/sqrt/div/exp/atan2/fmod/rsqrt forms mismatches (fast, strict) = {counts}"
 
 
 # ------------------------------------------------------------------------------------------------
 # golden fixtures from the reference: IW episodes (KAT2 / KAT4 and the rare-event cases)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("math_mode", MATH_MODES)
-@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_"))
+@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_") + golden_names("colav_stepniw_"))
 def test_iw_episode_matches_reference_golden(name, math_mode):
     g = golden(name)
     meta = json.loads(str(g["meta"]))
@@ -86,7 +86,9 @@ def test_iw_episode_matches_reference_golden(name, math_mode):
             e = rel_err(product_ctrl_vec(env, role), g[key + "_ctrl"][j], CTRL_SCALE)
             assert e.max() < ctrl_tol, (name, j, key, "ctrl", e, ctrl_tol)
         assert rel_err(float(env.env_f64[L.EF["travel_dist"], 0]), g["travel_dist"][j], 1.0) < tol
-        np.testing.assert_allclose(o, g["obs"][j], rtol=2e-7 * loose, atol=1e-6 * loose)
+        # (six observation entries in MultiShipNonIWEnv, colav_stepniw_*; the fixture rows are zero-padded to eight)
+        np.testing.assert_allclose(o, g["obs"][j][:len(o)], rtol=2e-7 * loose, atol=1e-6 * loose)
+        assert len(o) == (6 if meta["kind"] == "noniw_step" else 8)
         if is_rl:
             assert rel_err(r, g["reward"][j], 1e-3) < 1e-8 * loose, (name, j, r, g["reward"][j])
     if widened:
@@ -264,21 +266,25 @@ def test_batched_rl_episodes_match_reference(fixture, math_mode):
 
 @pytest.mark.parametrize("math_mode", MATH_MODES)
 @pytest.mark.parametrize("collav", ["none", "simple", "sbmpc"])
-def test_batched_colav_episodes_match_oracle(collav, math_mode):
+@pytest.mark.parametrize("iw", [True, False], ids=["MultiShipEnv", "MultiShipNonIWEnv"])
+def test_batched_colav_episodes_match_oracle(iw, collav, math_mode):
     """Simple model (config 2's env): 256 environments, per-env random scoping angles and jittered start positions,
     full episodes (9 step() calls); every environment is compared with its own scalar oracle run -- flags bit-exact,
-    states within 1e-9, no allowance of any kind."""
+    states within 1e-9, no allowance of any kind.  Both run_colav env classes: MultiShipEnv, and MultiShipNonIWEnv
+    driven with step(action) (run_colav/env.py:678-800: collision avoidance on both ships, no travel tracker,
+    six-entry observation)."""
     B = 256
     args = S.get_env_args(time_step=4, collav_mode=collav)
-    assets, m = S.build_colav_assets(args, iw=True)
+    route = dict() if iw else dict(obs_route="obs_ship_route.txt")
+    assets, m = S.build_colav_assets(args, iw=iw, **route)
     init = S.jittered_init_states(assets, B, pos_jitter_m=100.0, seed=1)
-    env, assets = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init, math_mode=math_mode)
+    env, assets = S.prepare_colav_env(args, iw=iw, num_envs=B, init_states=init, math_mode=math_mode, **route)
     gen = torch.Generator().manual_seed(0)
     actions = (torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6)
     actions[: B // 4] *= 0.1          # small angles keep the ships on a collision course
     env.reset()
     init_np = init.cpu().numpy().reshape(7, B, 2)
-    base_cfg = _oracle_cfg(assets, env, O.ENV_COLAV_IW)
+    base_cfg = _oracle_cfg(assets, env, O.ENV_COLAV_IW if iw else O.ENV_COLAV_NONIW)
     oracles = []
     for b in range(B):
         cfg = O.EnvConfig()
@@ -321,9 +327,10 @@ def test_batched_colav_episodes_match_oracle(collav, math_mode):
                 alive[b] = False
                 # finished environments are left alone by later calls
     assert not alive.any()
-    print(f"[colav/{collav}/{math_mode}] worst rel err {worst:.2e}")
-    # the batch must have exercised several different endings
-    assert bin(seen_events).count("1") >= 5, bin(seen_events)
+    print(f"[{'colav' if iw else 'noniw-step'}/{collav}/{math_mode}] worst rel err {worst:.2e}, events {seen_events:#x}")
+    # the batch must have exercised several different endings (the NonIW class has no travel tracker, hence no
+    # obstacle-ship navigation failure by distance travelled)
+    assert bin(seen_events).count("1") >= (5 if iw else 3), bin(seen_events)
     env.close()
 
 
@@ -634,6 +641,28 @@ def test_step_after_budget_raises_like_reference():
     with pytest.raises(UnboundLocalError):
         env2.step(np.array([0.0]))
     env.close(); env2.close()
+
+
+def test_noniw_step_needs_a_sampled_route_controller():
+    """MultiShipNonIWEnv.step(action) calls auto_pilot.update_route (run_colav/env.py:602), which only
+    HeadingBySampledRouteController has: with the plain HeadingByRouteController the reference raises AttributeError,
+    and the C ABI refuses the call (SHIPENV_E_STATE) instead of sampling into a route that cannot take waypoints."""
+    from ast_sac_b200.sim.controllers import HeadingByRouteController, HeadingControllerGains
+    args = S.get_env_args(time_step=4)
+    assets, m = S.build_colav_assets(args, iw=False)
+    assets[1].auto_pilot = HeadingByRouteController(
+        S.get_data_path("obs_ship_route_nonIW.txt"), heading_controller_gains=HeadingControllerGains(kp=.65, ki=0.001, kd=50),
+        los_parameters=S._los(args), time_step=args.time_step, max_rudder_angle=np.deg2rad(30))
+    from ast_sac_b200.env import MultiShipNonIWEnv
+    env = MultiShipNonIWEnv(assets=assets, map=m, args=args)
+    env.reset()
+    with pytest.raises(AttributeError):
+        env.step(np.array([0.0]))
+    a = torch.zeros(1, dtype=torch.float64, device="cuda")
+    assert L.load().shipenv_step(env._handle, a.data_ptr(), None) == 3      # SHIPENV_E_STATE
+    o, d, info = env._step()            # the class's own stepping is unaffected
+    assert not d and len(o) == 6
+    env.close()
 
 
 def test_pickle_roundtrip_rebuilds_device_state():

@@ -77,7 +77,7 @@ def test_host_objects_reproduce_reference_config(name):
     g = golden(name)
     meta = json.loads(str(g["meta"]))
     assets, m, args = assets_from_meta(meta)
-    kind = {"rl": O.ENV_RL, "colav": O.ENV_COLAV_IW, "noniw": O.ENV_COLAV_NONIW}[meta["kind"]]
+    kind = {"rl": O.ENV_RL, "colav": O.ENV_COLAV_IW, "noniw": O.ENV_COLAV_NONIW, "noniw_step": O.ENV_COLAV_NONIW}[meta["kind"]]
     cfg = O.env_config_from_assets(assets, m, args, kind)
     assert np.array_equal(_struct_bytes(cfg), g["cfg"])
 

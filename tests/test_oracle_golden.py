@@ -97,7 +97,7 @@ def _run_iw(name):
     return n_sub
 
 
-@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_"))
+@pytest.mark.parametrize("name", golden_names("colav_iw_") + golden_names("rl_") + golden_names("colav_stepniw_"))
 def test_iw_episode(name):
     _run_iw(name)
 
