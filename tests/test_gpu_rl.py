@@ -60,8 +60,18 @@ def test_batched_rollout_matches_reference_sampler_golden(name):
     env.close()
 
 
-def test_collector_fills_gpu_replay_buffer_and_sac_trains():
-    """config 5 in miniature: GPU-resident rollouts -> GPU replay buffer -> SAC updates, nothing on the host."""
+def test_collector_fills_gpu_replay_buffer_and_sac_trains(tmp_path):
+    """config 5 in miniature: GPU-resident rollouts -> GPU replay buffer -> SAC updates, nothing on the host; the run
+    directory (progress.csv, params.pkl with the pickled env, variant.json, debug.log) has the format of the
+    reference's logger (tests/golden/progress_format.json, from a run of the unmodified reference)."""
+    import csv
+    import json
+    import os
+    from ast_sac_b200.rl.logging import Logger, setup_logger
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "progress_format.json")))
+    lg = Logger()
+    lg.set_print(False)
+    run_dir = setup_logger("ast-sac_maritime_logs", variant=ref["variant"], base_log_dir=str(tmp_path), target=lg)
     torch.manual_seed(0)
     B = 2048
     args = S.get_env_args(time_step=4, collav_mode="none")
@@ -78,8 +88,18 @@ def test_collector_fills_gpu_replay_buffer_and_sac_trains():
     logs = []
     alg = BatchRLAlgorithm(tr, expl, evalc, buf, batch_size=256, max_path_length=9, num_epochs=2,
                            num_eval_steps_per_epoch=180, num_expl_steps_per_train_loop=4096,
-                           num_trains_per_train_loop=20, min_num_steps_before_training=8192, log=logs.append)
+                           num_trains_per_train_loop=20, min_num_steps_before_training=8192, log=logs.append, logger=lg)
     hist = alg.train()
+    lg.close()
+    rows = list(csv.reader(open(os.path.join(run_dir, "progress.csv"))))
+    assert rows[0] == ref["progress_columns"] and len(rows) == 3 and sorted(os.listdir(run_dir)) == ref["files"]
+    snap = torch.load(os.path.join(run_dir, "params.pkl"), weights_only=False)      # rebuilds the pickled env on the GPU
+    assert sorted(snap.keys()) == ref["snapshot_keys"]
+    assert {k: type(v).__name__ for k, v in snap.items()} == ref["snapshot_types"]
+    assert snap["exploration/env"].wrapped_env.num_envs == B
+    snap["exploration/env"].wrapped_env.close()
+    if snap["evaluation/env"] is not snap["exploration/env"]:
+        snap["evaluation/env"].wrapped_env.close()
     assert hist[-1]['replay_buffer/size'] >= 8192 + 2 * 4096
     assert buf._observations.device.type == "cuda" and buf.random_batch(256)["rewards"].device.type == "cuda"
     assert all(np.isfinite(v) for k, v in hist[-1].items() if k.startswith("trainer/"))

@@ -223,3 +223,64 @@ def test_batch_rl_algorithm_runs_on_fake_env():
     assert len(hist) == 2 and logs[1]['epoch'] == 1
     assert hist[1]['replay_buffer/size'] >= 100 + 2 * 60
     assert tr._n_train_steps_total == 6 and 'trainer/QF1 Loss' in hist[0]
+
+
+def test_run_directory_has_the_reference_loggers_format(tmp_path):
+    """progress.csv / variant.json / debug.log / params.pkl of a training run.  The fixture
+    tests/golden/progress_format.json was written by tests/golden/make_progress_golden.py from a run of the UNMODIFIED
+    reference's TorchBatchRLAlgorithm + logger (two miniature epochs, snapshot mode 'last'): same file list, the same
+    86 csv columns in the same (sorted) order, one row per epoch, the same snapshot keys."""
+    import csv
+    import json
+    import os
+
+    from ast_sac_b200.rl.logging import Logger, setup_logger
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "progress_format.json")))
+    torch.manual_seed(3)
+    env = NormalizedBoxEnv(FakeBatchedEnv(8), reward_scale=0.75)
+    pol = TanhGaussianPolicy([16, 16], obs_dim=8, action_dim=1)
+    qs = [ConcatMlp([16, 16], 1, 9) for _ in range(4)]
+    buf = GpuReplayBuffer(1000, env=env, device="cpu", seed=0)
+    tr = SACTrainer(env, pol, *qs, discount=0.965, reward_scale=0.75)
+    lg = Logger()
+    lg.set_print(False)
+    variant = dict(ref["variant"])
+    run_dir = setup_logger("ast-sac_maritime_logs", variant=variant, base_log_dir=str(tmp_path), target=lg, seed=5)
+    # <base>/<prefix with '-'>/<prefix>_<timestamp>_<id>--s-<seed> (launcher_utils.py:181-225)
+    assert os.path.basename(os.path.dirname(run_dir)) == "ast-sac-maritime-logs"
+    assert os.path.basename(run_dir).startswith("ast-sac_maritime_logs_") and run_dir.endswith("_0000--s-5")
+    # save_env_in_snapshot: the fake env is a plain picklable object like the real one
+    alg = BatchRLAlgorithm(tr, VectorizedPathCollector(env, pol, replay_buffer=buf),
+                           VectorizedPathCollector(env, MakeDeterministic(pol)), buf, batch_size=8, max_path_length=9,
+                           num_epochs=2, num_eval_steps_per_epoch=9, num_expl_steps_per_train_loop=9,
+                           num_trains_per_train_loop=2, min_num_steps_before_training=9, log=lambda s: None, logger=lg)
+    alg.train()
+    lg.close()
+    assert sorted(os.listdir(run_dir)) == ref["files"]
+    rows = list(csv.reader(open(os.path.join(run_dir, "progress.csv"))))
+    assert rows[0] == ref["progress_columns"]
+    assert len(rows) - 1 == ref["progress_rows"] == 2
+    assert all(len(r) == len(rows[0]) and all(c != "" for c in r) for r in rows[1:])
+    col = {k: i for i, k in enumerate(rows[0])}
+    assert [r[col["Epoch"]] for r in rows[1:]] == ["0", "1"] and [r[col["epoch"]] for r in rows[1:]] == ["0", "1"]
+    assert int(rows[2][col["trainer/num train calls"]]) == 4
+    assert float(rows[2][col["expl/num steps total"]]) >= 27 and float(rows[1][col["eval/Num Paths"]]) >= 1
+    snap = torch.load(os.path.join(run_dir, "params.pkl"), weights_only=False)
+    assert sorted(snap.keys()) == ref["snapshot_keys"]
+    assert {k: type(v).__name__ for k, v in snap.items()} == ref["snapshot_types"]
+    assert json.load(open(os.path.join(run_dir, "variant.json"))) == ref["variant"]
+    # later dumps with other keys keep the first dump's columns (logging.py:287-300)
+    lg2 = Logger()
+    lg2.set_print(False)
+    lg2.add_tabular_output(str(tmp_path / "t.csv"))
+    lg2.record_dict(dict(b=1, a=2)); lg2.dump_tabular()
+    lg2.record_dict(dict(b=3, c=4)); lg2.dump_tabular()
+    lg2.close()
+    assert open(tmp_path / "t.csv").read().splitlines() == ["a,b", "2,1", ",3"]
+    # snapshot modes (logging.py:314-336)
+    lg3 = Logger()
+    lg3.set_snapshot_dir(str(tmp_path)); lg3.set_snapshot_mode("gap_and_last"); lg3.set_snapshot_gap(2)
+    for itr in range(3):
+        lg3.save_itr_params(itr, dict(x=itr))
+    assert sorted(f for f in os.listdir(tmp_path) if f.endswith(".pkl")) == ["itr_0.pkl", "itr_2.pkl", "params.pkl"]
+    assert torch.load(tmp_path / "params.pkl", weights_only=False) == dict(x=2)

@@ -46,6 +46,11 @@ def parse():
     p.add_argument('--clip_val', type=float, default=100)
     p.add_argument('--seed', type=int, default=0)
     p.add_argument('--cuda_graph', type=int, default=1, help="replay each SAC update as one CUDA graph (0: eager)")
+    p.add_argument('--do_logging', type=int, default=0,
+                   help="write the run directory of the reference's logger: progress.csv, variant.json, debug.log, "
+                        "params.pkl (ast-sac_runner.py:240-241; ast_sac_b200/rl/logging.py)")
+    p.add_argument('--base_log_dir', type=str, default=None, help="default: ./run/logs like the reference")
+    p.add_argument('--snapshot_mode', type=str, default='last')
     return p.parse_args()
 
 
@@ -68,6 +73,24 @@ def main():
                          capturable=bool(a.cuda_graph))
     expl = VectorizedPathCollector(wrapped, policy, replay_buffer=buf)
     evalc = VectorizedPathCollector(wrapped, MakeDeterministic(policy))
+    run_logger = None
+    if a.do_logging:
+        from ast_sac_b200.rl.logging import logger as run_logger, setup_logger
+        variant = dict(   # run/ast-sac_runner.py:211-236
+            algorithm="SAC", version="normal", layer_size=a.layer_size, replay_buffer_size=a.replay_buffer_size,
+            algorithm_kwargs=dict(num_epochs=a.num_epochs, num_eval_steps_per_epoch=a.num_eval_steps_per_epoch,
+                                  num_trains_per_train_loop=a.num_trains_per_train_loop,
+                                  num_expl_steps_per_train_loop=a.num_expl_steps_per_train_loop,
+                                  min_num_steps_before_training=a.min_num_steps_before_training,
+                                  max_path_length=a.max_path_length, batch_size=a.batch_size),
+            trainer_kwargs=dict(discount=a.discount, soft_target_tau=a.soft_target_tau,
+                                target_update_period=a.target_update_period, policy_lr=a.policy_lr, qf_lr=a.qf_lr,
+                                reward_scale=a.reward_scale, use_automatic_entropy_tuning=True,
+                                action_reg_coeff=a.action_reg_coeff, clip_val=a.clip_val))
+        run_logger.set_print(False)
+        run_dir = setup_logger('ast-sac_maritime_logs', variant=variant, base_log_dir=a.base_log_dir,
+                               snapshot_mode=a.snapshot_mode, seed=a.seed)
+        print(json.dumps({"run_dir": run_dir}), flush=True)
     c0 = env.total_substeps()
     t0 = time.perf_counter()
     alg = BatchRLAlgorithm(trainer, expl, evalc, buf, batch_size=a.batch_size, max_path_length=a.max_path_length,
@@ -75,7 +98,8 @@ def main():
                            num_expl_steps_per_train_loop=a.num_expl_steps_per_train_loop,
                            num_trains_per_train_loop=a.num_trains_per_train_loop,
                            min_num_steps_before_training=a.min_num_steps_before_training,
-                           log=lambda s: print(json.dumps(s), flush=True), use_cuda_graph=bool(a.cuda_graph))
+                           log=lambda s: print(json.dumps(s), flush=True), use_cuda_graph=bool(a.cuda_graph),
+                           logger=run_logger)
     hist = alg.train()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
