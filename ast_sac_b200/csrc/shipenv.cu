@@ -583,8 +583,9 @@ int shipenv_set_params(shipenv_t* h, const ShipEnvParams* params) {
     // change numbers (gains, time steps, the dt_shaft of the reset quirk, the map), not what the state means
     if (params->ship[0].model_kind != h->params.ship[0].model_kind || params->env_kind != h->params.env_kind ||
         params->ship[0].n_wp != h->params.ship[0].n_wp || params->ship[1].n_wp != h->params.ship[1].n_wp ||
-        params->max_sampling_frequency != h->params.max_sampling_frequency || params->math_mode != h->params.math_mode)
-      return fail(SHIPENV_E_STATE, "model_kind, env_kind, route lengths, max_sampling_frequency and math_mode cannot "
+        params->max_sampling_frequency != h->params.max_sampling_frequency || params->math_mode != h->params.math_mode ||
+        params->obs_sampled_route != h->params.obs_sampled_route)
+      return fail(SHIPENV_E_STATE, "model_kind, env_kind, route lengths, max_sampling_frequency, obs_sampled_route and math_mode cannot "
                                    "change once the environments are constructed: create a new handle");
   }
   CUDA_TRY(cudaSetDevice(h->device));

@@ -44,6 +44,9 @@
 #ifndef SENV_VMAG_RSQRT
 #define SENV_VMAG_RSQRT 1   // fast build: relative wind speed as x * rsqrt(x), within 2 ulp (3 links fewer: +0.6 %)
 #endif
+#ifndef SENV_RUDDER_REASSOC
+#define SENV_RUDDER_REASSOC 1
+#endif
 #ifndef SENV_SEG_SMEM
 #define SENV_SEG_SMEM 0     // LOS segment cache in shared memory instead of 14 registers (measured: colav_iw +0.9 %,
                             // rl -2 %, one step per launch +4 %; profiles/r02_ncu_summary.md part 5)
@@ -362,8 +365,17 @@ __device__ __forceinline__ void ship_step(const ShipEnvShipParams& P, const Rout
   const double u_c = cpsi * H.cur_n + spsi * H.cur_e;
   const double v_c = (-spsi) * H.cur_n + cpsi * H.cur_e;
   const double u_r = u - u_c, v_r = v - v_c;
-  const double f_rudder_v = -H.c_rudder_v * rudder * (u - u_c);
-  const double f_rudder_r = -H.c_rudder_r * rudder * (u - u_c);
+  double f_rudder_v, f_rudder_r;
+  if (SENV_FAST_MATH && SENV_RUDDER_REASSOC && MODEL == SHIPENV_MODEL_SIMPLE) {
+    // (-c (u - u_c)) * rudder instead of (-c rudder) * (u - u_c): the factor without the rudder angle is ready early, so
+    // the force follows the angle -- the end of the step's longest chain -- by one FP64 link instead of two.  Simple
+    // model only: its block's static schedule shrinks from 767 to 718 cycles, the detailed model's grows (745 -> 767).
+    f_rudder_v = (-H.c_rudder_v * (u - u_c)) * rudder;
+    f_rudder_r = (-H.c_rudder_r * (u - u_c)) * rudder;
+  } else {
+    f_rudder_v = -H.c_rudder_v * rudder * (u - u_c);
+    f_rudder_r = -H.c_rudder_r * rudder * (u - u_c);
+  }
   // --- wind (get_wind_force, ship_model.py:162-175)
 #if SENV_FAST_MATH
   // u_rw = ws*cos(wd - psi) - u, v_rw = ws*sin(wd - psi) - v with the angle-difference identity;
@@ -1988,5 +2000,6 @@ cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st)
 
 #else
 template __global__ void k_env<0, 1, 0, 0>(DevView, const double*, int, unsigned long long*);
+template __global__ void k_env<1, 2, 0, 0>(DevView, const double*, int, unsigned long long*);
 #endif
 }  // namespace SENV_NS
