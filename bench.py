@@ -429,6 +429,11 @@ def roofline_block(workload, collav, B, m, n_episodes, fp64_peak):
         "peak_source": "DFMA microbenchmark measured live in this run (MEASURED_PEAKS.json has no FP64 entry)",
         "flop_per_env_step_executed": flop_exec, "flop_per_env_step_algorithmic": FLOP_ALGO[workload] if collav == "none" else None,
         "achieved_algorithmic": algo,
+        "frac_algorithmic": None if algo is None else algo / fp64_peak,
+        # ncu's own view of the binding unit in the capture the counts come from: DMUL / DADD / DSETP hold the FP64
+        # pipe as long as a DFMA but count one / one / zero flop, so the pipe is busier than `frac` says
+        "fp64_pipe_active_pct_ncu": None if (counts is None or stale) else counts.get("pipe_fp64_pct"),
+        "issue_slots_active_pct_ncu": None if (counts is None or stale) else counts.get("issue_active_pct"),
         "counts_source": None if counts is None else counts.get("source"),
         "traffic": None if (counts is None or stale or B != counts.get("envs")) else counts.get("dram_bytes_per_launch"),
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/)",

@@ -55,12 +55,16 @@ def main():
                 v = col(hdr, r, f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed") * cyc
             return v
         dfma, dadd, dmul = total("dfma"), total("dadd"), total("dmul")
-        dram = col(hdr, r, "dram__bytes_read.sum", 0.0) + col(hdr, r, "dram__bytes_write.sum", 0.0)
-        # ncu prints byte counts in the unit of the units row; normalise to bytes
-        unit = rows[1][hdr.index("dram__bytes_read.sum")] if "dram__bytes_read.sum" in hdr else "byte"
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+        # ncu prints every byte count in the unit of ITS OWN column of the units row (the write count of a launch that
+        # writes little comes in Kbyte next to a read count in Mbyte)
+        def dram_bytes(name):
+            if name not in hdr:
+                return 0.0
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(rows[1][hdr.index(name)], 1.0)
+            return col(hdr, r, name, 0.0) * scale
+        dram = dram_bytes("dram__bytes_read.sum") + dram_bytes("dram__bytes_write.sum")
         out.append({"env_steps": n, "fp64_inst_per_env_step": (dfma + dadd + dmul) / n,
-                    "flop_exec_per_env_step": (2 * dfma + dadd + dmul) / n, "dram_bytes": dram * scale,
+                    "flop_exec_per_env_step": (2 * dfma + dadd + dmul) / n, "dram_bytes": dram,
                     "pipe_fp64_pct": col(hdr, r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                     "issue_active_pct": col(hdr, r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                     "achieved_occupancy_pct": col(hdr, r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
