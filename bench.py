@@ -73,7 +73,7 @@ def kernel_counts(workload: str, collav: str):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)     # 20 bench steps = 160 episodes: a timed region of ~1 s at 1e5 envs
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--envs", type=int, default=100_000, help="environments per GPU")
     ap.add_argument("--episodes-per-step", type=int, default=8,
