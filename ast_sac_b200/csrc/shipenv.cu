@@ -65,6 +65,7 @@ struct shipenv {
   long long log_envs = 0, log_capacity = 0;
   unsigned* grid_dev = nullptr;       // culling grid cells
   unsigned long long* edges_dev = nullptr;   // per-cell ring-segment masks
+  float* safe_dev = nullptr;                 // per-cell safe radius (SenvGrid::safe)
   SenvGrid grid{};
   // staging for the *_host entry points
   double* act_dev = nullptr;
@@ -236,7 +237,7 @@ int build_grid(shipenv* h) {
   const double w = p.map_max_e - p.map_min_e, ht = p.map_max_n - p.map_min_n;
   int nx = 1, ny = 1;
   double cell = 1.0;
-  if (p.n_poly > 0 && w > 0 && ht > 0) {
+  if (w > 0 && ht > 0) {   // (without polygons the masks are empty; the safe radius still knows the map horizon)
     cell = std::fmax(std::fmax(w, ht) / 256.0, 50.0);
     nx = (int)std::ceil(w / cell);
     ny = (int)std::ceil(ht / cell);
@@ -288,10 +289,29 @@ int build_grid(shipenv* h) {
           edges[((size_t)iy * nx + ix) * 2 + (i >> 6)] |= 1ull << (i & 63);
       }
     }
+  // safe radius per cell (SenvGrid::safe): the ring distance is 1-Lipschitz, so every point of the cell is at least
+  // d(centre) - half diagonal from every ring; a ship whose centre is outside every polygon and further than half a
+  // diagonal of its L x L square from every ring has no corner inside one
+  std::vector<float> safe((size_t)nx * ny, 0.f);
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+      const double cx = p.map_min_e + (ix + 0.5) * cell, cy = p.map_min_n + (iy + 0.5) * cell;
+      double dmin = 1e9;
+      bool in_poly = false;
+      for (int q = 0; q < p.n_poly; ++q) {
+        dmin = std::fmin(dmin, host_ring_distance(p, q, cx, cy));
+        in_poly = in_poly || host_poly_contains(p, q, cx, cy);
+      }
+      const double r = 0.999 * (dmin - halfdiag - half_len * 1.4142135623730951 - 1.0);
+      safe[(size_t)iy * nx + ix] = (!in_poly && r > 0.0) ? (float)r : 0.f;
+    }
   // allocate and fill the new tables first; the handle keeps its old ones if anything fails
   unsigned* cells_dev = nullptr;
   unsigned long long* edges_dev = nullptr;
+  float* safe_dev = nullptr;
   cudaError_t e = cudaMalloc(&cells_dev, cells.size() * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&safe_dev, safe.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(safe_dev, safe.data(), safe.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&edges_dev, edges.size() * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemcpy(cells_dev, cells.data(), cells.size() * sizeof(unsigned), cudaMemcpyHostToDevice);
   if (e == cudaSuccess)
@@ -299,13 +319,16 @@ int build_grid(shipenv* h) {
   if (e != cudaSuccess) {
     cudaFree(cells_dev);
     cudaFree(edges_dev);
+    cudaFree(safe_dev);
     return fail(SHIPENV_E_CUDA, "uploading the map culling grid: %s", cudaGetErrorString(e));
   }
   cudaFree(h->grid_dev);
   cudaFree(h->edges_dev);
+  cudaFree(h->safe_dev);
   h->grid_dev = cells_dev;
   h->edges_dev = edges_dev;
-  h->grid = SenvGrid{h->grid_dev, h->edges_dev, p.map_min_e, p.map_min_n, 1.0 / cell, (double)nx, (double)ny, nx, ny};
+  h->safe_dev = safe_dev;
+  h->grid = SenvGrid{h->grid_dev, h->edges_dev, h->safe_dev, p.map_min_e, p.map_min_n, 1.0 / cell, (double)nx, (double)ny, nx, ny};
   return SHIPENV_OK;
 }
 
@@ -462,6 +485,7 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
     cudaFree(h->staged_dev);
     cudaFree(h->grid_dev);
     cudaFree(h->edges_dev);
+    cudaFree(h->safe_dev);
     cudaFree(h->queue_dev);
     if (h->done_host) cudaFreeHost(h->done_host);
     cudaGetLastError();
@@ -488,6 +512,7 @@ int shipenv_destroy(shipenv_t* h) {
   cudaFree(h->staged_dev);
   cudaFree(h->grid_dev);
   cudaFree(h->edges_dev);
+  cudaFree(h->safe_dev);
   cudaFree(h->queue_dev);
   if (h->done_host) cudaFreeHost(h->done_host);
   cudaFree(h->act_dev);

@@ -38,6 +38,9 @@
 #ifndef SENV_MIN_BLOCKS
 #define SENV_MIN_BLOCKS 4   // resident CTAs per SM the env kernel is compiled for (128 registers/thread)
 #endif
+#ifndef SENV_MIN_BLOCKS_QUIET
+#define SENV_MIN_BLOCKS_QUIET SENV_MIN_BLOCKS   // the same for the instantiations with quiet steps (SENV_QUIET)
+#endif
 #ifndef SENV_ENV_BLOCK
 #define SENV_ENV_BLOCK 128  // threads per CTA of the env kernel
 #endif
@@ -50,6 +53,9 @@
 #ifndef SENV_SEG_SMEM
 #define SENV_SEG_SMEM 0     // LOS segment cache in shared memory instead of 14 registers (measured: colav_iw +0.9 %,
                             // rl -2 %, one step per launch +4 %; profiles/r02_ncu_summary.md part 5)
+#endif
+#ifndef SENV_QUIET
+#define SENV_QUIET 1        // env kernel: event tests skipped while every lane of the warp is provably far from any event (k_env)
 #endif
 #ifndef SENV_LOS_RSQRT
 #define SENV_LOS_RSQRT 1    // fast build: e_ct / sqrt(R^2 - e_ct^2) as e_ct * rsqrt(.) (11 dependent FP64 links fewer: +5 %)
@@ -474,6 +480,16 @@ __device__ __forceinline__ unsigned map_cell_masks(const MapView& mp, double n_p
   const int ix = (int)(inside ? fx : 0.0), iy = (int)(inside ? fy : 0.0);
   const unsigned m = __ldg(mp.grid.cells + iy * mp.grid.nx + ix);
   return inside ? m : (all | (all << 16));
+}
+
+// Safe radius of the cell the point lies in (SenvGrid::safe): a ship that has moved less than this from the point
+// cannot be grounded.  0 outside the grid (or NaN).  Single precision: a position within a millimetre of a cell border
+// may read the neighbouring cell's radius, which is off by that millimetre at most.
+__device__ __forceinline__ float map_safe_radius(const MapView& mp, float n_pos, float e_pos) {
+  const float fx = (e_pos - (float)mp.grid.e0) * (float)mp.grid.inv_cell;
+  const float fy = (n_pos - (float)mp.grid.n0) * (float)mp.grid.inv_cell;
+  if (!(fx >= 0.0f && fy >= 0.0f && fx < (float)mp.grid.nx && fy < (float)mp.grid.ny)) return 0.0f;
+  return __ldg(mp.grid.safe + (int)fy * mp.grid.nx + (int)fx);
 }
 
 // Polygon.contains(Point(x, y)) for one polygon: even-odd crossing rule
@@ -1282,6 +1298,7 @@ k_prologue(DevView dv, const double* __restrict__ actions, unsigned long long* _
 // ------------------------------------------------------------------------------------------------
 enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 
+
 #ifndef SENV_MIN_BLOCKS_SBMPC
 #define SENV_MIN_BLOCKS_SBMPC 4   // measured: 3 CTAs/SM (168 registers, fewer spills) speeds the inactive steps up but slows the evaluation
 #endif
@@ -1289,7 +1306,9 @@ template <int MODEL, int ENVKIND, int MODE, int COLLAV>
 #ifdef SENV_MAXNREG
 __global__ void __maxnreg__(SENV_MAXNREG)
 #else
-__global__ void __launch_bounds__(SENV_ENV_BLOCK, COLLAV == SHIPENV_COLLAV_SBMPC ? SENV_MIN_BLOCKS_SBMPC : SENV_MIN_BLOCKS)
+__global__ void __launch_bounds__(SENV_ENV_BLOCK, COLLAV == SHIPENV_COLLAV_SBMPC ? SENV_MIN_BLOCKS_SBMPC
+                                  : ((SENV_QUIET != 0) && COLLAV == SHIPENV_COLLAV_NONE && ENVKIND == SHIPENV_ENV_COLAV_IW)
+                                        ? SENV_MIN_BLOCKS_QUIET : SENV_MIN_BLOCKS)
 #endif
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
   constexpr bool SBMPC = COLLAV == SHIPENV_COLLAV_SBMPC;
@@ -1323,6 +1342,8 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   const long long n_slots = ((long long)gridDim.x * blockDim.x) >> 1;
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
+  // Quiet steps (see the simulator loop): instantiations without collision avoidance and without a per-step reward
+  constexpr bool QUIET = (SENV_QUIET != 0) && COLLAV == SHIPENV_COLLAV_NONE && IS_IW && !IS_RL;
   // (the NonIW env samples intermediate waypoints too when it is driven with step(action), run_colav/env.py:678-800)
   const bool dynamic_route = (IS_IW || G.obs_sampled_route != 0) && role == 1;
   const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
@@ -1333,6 +1354,12 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
 
   long long env = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
   int lstate = (env < B) ? LS_LOAD : LS_IDLE;
+  // QUIET: distance this ship has travelled since it was loaded (`odo`), the reading at which one of the tests on its
+  // own position could change its outcome at the earliest (`lim`: map, route end, travel tracker, see own_budget; < 0:
+  // to be taken anew by the full evaluation), and the reading at which the pair could collide at the earliest
+  double odo = 0.0, lim = (env < B) ? -1.0 : 1e30, coll_lim = 1e30;
+  // QUIET: squared distance to this ship's next waypoint at or below which a waypoint test can fire (-1: none applies)
+  double wp_thr2 = -1.0;
 
   // registers of the environment currently held by this lane
   Ship s = Ship{};
@@ -1366,9 +1393,56 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   bool have_obs = false;      // next_observations was assigned by this call
   int stage = 0;              // MODE_STEP: 0 main loop, 1 extra step after RoA, 2 run to completion
   bool have_iw = false;
-  int k_left = 0;
+  int k_left = (QUIET && !(env < B)) ? (1 << 30) : 0;   // (QUIET, MODE_STEP: simulator steps until the time limit can bind)
   // metric counters over every environment this lane handled
   int total_sub = 0, total_fin = 0, total_dead = 0;
+#ifdef SENV_QUIET_STATS
+  int qs_total = 0, qs_quiet = 0;
+#endif
+  // QUIET: distance this ship may still travel from where it is before one of the tests on its OWN position can change
+  // its outcome: grounding (safe radius of the culling-grid cell), route end (max(|dn|, |de|) <= distance) and, for the
+  // obstacle ship, the travel tracker (which lags the position by the step just taken).  A stopped ship's bits stay as
+  // they are.  (The map horizon is not among them: ships sail along it for hundreds of steps, so the quiet steps test
+  // it as it stands.)
+  // (single precision: the margin of 2 m covers its rounding at map scale many times over; a NaN position makes the
+  // odometer NaN, which no limit passes)
+  auto own_budget = [&](double north, double east) -> float {
+    if (has_stop_branch && s.stop) return 1e30f;
+    const float n = (float)north, e = (float)east;
+    float b = map_safe_radius(mp, n, e);
+    b = fminf(b, fmaxf(fabsf(n - (float)route_end_n), fabsf(e - (float)route_end_e)) - 200.0f);
+    if (role == 1) b = fminf(b, (float)(sb.seg_len2 - travel_dist - pending_dist));
+    return 0.999f * b - 2.0f;
+  };
+  // QUIET: everything a lane holds for the quiet steps, taken anew from the state after a step (or after the load);
+  // (pn, pe) is where the partner ship is.  Every term is a lower bound, 1-Lipschitz in the ship's position, of the
+  // distance to a threshold, less a margin that covers the rounding of the running sum.
+  auto take_limit = [&](double pn, double pe) {
+    const Derived& D = derived_of(P);
+    const bool stopped = has_stop_branch && s.stop;           // this ship no longer moves: its own bits stay as they are
+    // the waypoint tests of the quiet steps: `<= ra^2` for the autopilot's switch, `< roa^2` for the env's radius of
+    // acceptance (taken as `<=`: a step with equality is evaluated in full)
+    wp_thr2 = -1.0;
+    if (!stopped) {
+      if (s.n_wp > s.k + 1) wp_thr2 = D.los_ra2;
+      if (MODE == MODE_STEP && role == 1 && stage == 0) wp_thr2 = fmax(wp_thr2, sb.roa2);
+    }
+    // collision (d < 50): either ship may close half the gap; max(|dn|, |de|) <= d
+    const float gap = fmaxf(fabsf((float)(pn - s.north)), fabsf((float)(pe - s.east)));
+    coll_lim = odo + (double)(0.4995f * (gap - 50.0f) - 2.0f);
+    lim = odo + (double)own_budget(s.north, s.east);
+    // simulation time limit on the test ship's clock (a stopped ship's clock advances twice per step)
+    int cap = 1 << 30;
+    if (role == 0) {
+      const float left = __fdividef((float)(D.sim_time - s.time), (float)(2.0 * D.dt)) - 4.0f;
+      cap = (left > 0.0f) ? ((left < 1e9f) ? (int)left : (1 << 30)) : 0;
+    }
+    if (MODE == MODE_STEP) {
+      k_left = cap;
+    } else if (cap < k_left) {
+      lim = -1.0;
+    }
+  };
 
   for (;;) {
     // ---------------- (1) fetch: lane pairs without an environment pull the next index
@@ -1388,6 +1462,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         if (lstate == LS_FETCH) {
           env = mine;
           lstate = (env < B) ? LS_LOAD : LS_IDLE;
+          if (QUIET && lstate == LS_IDLE) { lim = 1e30; coll_lim = 1e30; odo = 0.0; k_left = 1 << 30; wp_thr2 = -1.0; s.e_ct = 0.0; }   // an idle lane never vetoes a quiet step
         }
       }
     }
@@ -1432,6 +1507,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       s.n_wp = P.n_wp + n_iw;
       last_stop_branch = false; out_reward = 0.0; out_info = 0; nsub = 0;
       have_obs = false; stage = 0; have_iw = false; k_left = k_substeps;
+      odo = 0.0; lim = -1.0;
       lstate = LS_RUN;
       if (flags & SHIPENV_FLAG_DONE) {
         // already done before this call: nothing changes except the step count of the call
@@ -1454,12 +1530,23 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         }
         tlog_n = log_begin(dv, env, sidx);
         if (CARRY_YAW_SC) senv_sincos(s.yaw, &yaw_sc.x, &yaw_sc.y);
+        if (QUIET) {
+          // the limits of the quiet steps, so that the first step after the load can already be one (the two lanes of
+          // the pair are here together)
+          const unsigned pair = 3u << (lane & ~1);
+          const double q_n = __shfl_xor_sync(pair, s.north, 1), q_e = __shfl_xor_sync(pair, s.east, 1);
+          take_limit(q_n, q_e);
+        }
       }
     }
 
     // ---------------- (3) simulator steps of the running lanes, until some pair has finished its call
     do {
+    quiet_next:;
     const bool running = (lstate == LS_RUN) && !finalize;
+    // QUIET: does this lane pass the coming step as a quiet one (see below); lanes that do not move keep their reading
+    if (QUIET) k_left -= 1;
+    bool lane_quiet = QUIET && (odo < lim) && (k_left > 0);
     // The assets step in list order (test_step, then obs_step).  The lanes of a pair run them side by
     // side, except under SBMPC in the NonIW env, where obs_step's SBMPC call reads the state the ship under
     // test has just integrated to (run_colav env.py:502-527): two phases there.
@@ -1528,7 +1615,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         s.time = s.time + dt;
         s.time = s.time + dt;
         last_stop_branch = true;
-        cell = map_cell_masks(mp, s.north, s.east);
+        if (!QUIET) cell = map_cell_masks(mp, s.north, s.east);
       } else {
         scratch.u_pre = s.u;
         last_stop_branch = false;
@@ -1541,9 +1628,33 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
         const double pre_n = s.north, pre_e = s.east;
         ship_step<MODEL, !EARLY_SWITCH, SIMPLE>(P, rt, n_iw, s, hit, collav_bias, heading_offset, speed_factor,
                                                 log_next_row(dv, 2 * env + role, tlog_n),
-                                                [&](double new_n, double new_e) { cell = map_cell_masks(mp, new_n, new_e); },
+                                                [&](double new_n, double new_e) {
+                                                  if (!QUIET) { cell = map_cell_masks(mp, new_n, new_e); return; }
+                                                  // QUIET: the travel tracker (below) and this lane's part of the
+                                                  // quiet-step test, evaluated as soon as the kinematics have the new
+                                                  // position -- beside the step's long chains instead of behind them
+                                                  const bool track = (role == 1) && (flags & SHIPENV_FLAG_TRACKER);
+                                                  travel_dist += track ? pending_dist : 0.0;
+                                                  travel_time += track ? dt : 0.0;
+                                                  const double tn = new_n - s.north, te = new_e - s.east;
+                                                  pending_dist = SENV_SQRT(tn * tn + te * te);
+                                                  odo += pending_dist;
+                                                  const double qn = new_n - s.seg.wn(), qe = new_e - s.seg.we();
+                                                  const Derived& D = derived_of(P);
+                                                  const bool outside = ((int)(new_n < D.hz_min_n) | (int)(new_n > D.hz_max_n) |
+                                                                        (int)(new_e < D.hz_min_e) | (int)(new_e > D.hz_max_e)) != 0;
+                                                  // (combined without short-circuit branches: one basic block)
+                                                  lane_quiet = ((int)(k_left > 0) & (int)!(qn * qn + qe * qe <= wp_thr2) & (int)!outside) != 0;
+                                                },
                                                 CARRY_YAW_SC ? &yaw_sc : nullptr);
-        if (IS_IW) {
+        if (QUIET) {
+          // a lane that reaches its limit first takes its own part anew where it is now (a few instructions, no
+          // exchange with the partner lane): only a ship that really is next to one of its thresholds asks for the
+          // full evaluation.  (Behind the step, not inside it: a branch would split the step's basic block.)
+          if (!(odo < lim) && lim >= 0.0) lim = odo + (double)own_budget(s.north, s.east);
+          lane_quiet = lane_quiet && (odo < lim) && !(fabs(s.e_ct) > derived_of(P).nav_fail_tol);
+        }
+        if (IS_IW && !QUIET) {
           // travel tracker on the two last logged rows of the obstacle ship (env.py:526-534); evaluated without a
           // branch on the role (the test lane's copies are never read: a divergent branch would cost the same issue
           // slots and end the step's basic block)
@@ -1557,6 +1668,45 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
     }
     }
+    if (QUIET) {
+      // ---- quiet steps.  Every event test below is a predicate on where the two ships are (grounding, map horizon,
+      // route end, radius of acceptance, waypoint switch, collision, cross-track error, travelled distance) or on the
+      // clock.  The two that fire routinely are evaluated here as they stand: the distance to the ship's next waypoint
+      // against the larger of the radii that apply to it (`wp_thr2`: radius of acceptance of the env, of the autopilot)
+      // and the cross-track error against the navigation-failure tolerance.  For all the others each lane took, at its
+      // last full evaluation, the smallest distance its ship would have to travel before one of ITS predicates could
+      // flip (`lim`, see own_budget and the end of the loop body) and the number of steps before the time limit can bind
+      // (`k_left`).  While every lane of the warp passes after the step it just took, all the tests below are known to
+      // come out as they did -- "nothing holds" or, for a stopped ship, the same bits as before -- and the bookkeeping
+      // they drive changes nothing, so the warp goes straight to the next step.  Idle lanes hold an infinite limit.
+      // (MODE_SUBSTEPS: k_left is the launch's own step counter, so the last step of a launch is always evaluated in
+      // full.)
+#ifdef SENV_QUIET_STATS
+      qs_total += 1;
+#endif
+      if (__all_sync(FULL_MASK, lane_quiet && (odo < coll_lim))) {
+        nsub += 1;
+#ifdef SENV_QUIET_STATS
+        qs_quiet += 1;
+#endif
+        goto quiet_next;
+      }
+      if (__all_sync(FULL_MASK, lane_quiet)) {
+        // only collision limits ran out (two ships passing each other stay a few steps apart for a long time): the
+        // collision test as it stands -- same expressions as below -- and new limits from the gap that is left
+        const double c_north = shfl_xor_f64(s.north, 1), c_east = shfl_xor_f64(s.east, 1);
+        const double cx = c_north - s.north, cy = c_east - s.east;
+        const bool hit = running && (cx * cx + cy * cy < 2500.0);
+        if (running) coll_lim = odo + (double)(0.4995f * (fmaxf(fabsf((float)cx), fabsf((float)cy)) - 50.0f) - 2.0f);
+        if (!__any_sync(FULL_MASK, hit)) {
+          nsub += 1;
+#ifdef SENV_QUIET_STATS
+          qs_quiet += 1;
+#endif
+          goto quiet_next;
+        }
+      }
+    }
     // ---- the ships meet: positions both ways, then one word of partial flags per ship.  Almost every
     // simulator step is "quiet" (no termination / stop condition holds for either ship, no collision, no
     // radius of acceptance reached): those steps skip the event bookkeeping below altogether.
@@ -1567,19 +1717,27 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     int my_flags = 0;
     double ra = 0.0, rb = 0.0;
     if (running) {
-      const double len = derived_of(P).l_ship;
-      const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
-      // (four comparisons combined without short-circuit branches)
       const Derived& D = derived_of(P);
+      bool nav_fail = fabs(s.e_ct) > derived_of(P).nav_fail_tol;
+      // QUIET: a moving ship still inside its limit is known to fail every test on its own position (that is what the
+      // limit bounds), so a full evaluation that another lane of the warp asked for skips them -- and the culling-grid
+      // load in front of them -- for this lane
+      const bool known_clear = QUIET && (odo < lim) && !(has_stop_branch && s.stop);
+      // (four comparisons combined without short-circuit branches)
       const bool outside = ((int)(s.north < D.hz_min_n) | (int)(s.north > D.hz_max_n) |
                             (int)(s.east < D.hz_min_e) | (int)(s.east > D.hz_max_e)) != 0;
-      const double dn = s.north - route_end_n, de = s.east - route_end_e;
-      // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
-      // sqrt(nextafter(40000)) rounds above 200)
-      const bool reached = (dn * dn + de * de) <= 40000.0;
-      bool nav_fail = fabs(s.e_ct) > derived_of(P).nav_fail_tol;
-      if (role == 1) nav_fail = (travel_dist > sb.seg_len2) || (travel_time > INFINITY) || nav_fail;
-      my_flags = (grounding ? 1 : 0) | (nav_fail ? 2 : 0) | (reached ? 4 : 0) | (outside ? 8 : 0);
+      if (!known_clear) {
+        if (QUIET) cell = map_cell_masks(mp, s.north, s.east);
+        const double len = derived_of(P).l_ship;
+        const bool grounding = pos_inside_obstacles(mp, cell & 0xffffu, s.north, s.east, len);
+        const double dn = s.north - route_end_n, de = s.east - route_end_e;
+        // is_reaches_endpoint: sqrt(d2) <= 200  <=>  d2 <= 40000 exactly (sqrt is correctly rounded and
+        // sqrt(nextafter(40000)) rounds above 200)
+        const bool reached = (dn * dn + de * de) <= 40000.0;
+        if (role == 1) nav_fail = (travel_dist > sb.seg_len2) || (travel_time > INFINITY) || nav_fail;
+        my_flags = (grounding ? 1 : 0) | (reached ? 4 : 0);
+      }
+      my_flags |= (nav_fail ? 2 : 0) | (outside ? 8 : 0);
       // is_within_simu_time_limit on the test ship's clock (check_condition.py:206-213)
       if (role == 0 && s.time > derived_of(P).sim_time) my_flags |= 16;
       if (MODE == MODE_STEP && role == 1 && stage == 0) {
@@ -1699,8 +1857,10 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           st_done = ts && !terminal;
           if (role == 1 && os && !terminal) s.stop = 1;
         } else {                                                  // run_colav env.py:1385-1399
+          const int stop_before = s.stop;
           if (ts && !terminal) { if (role == 0) s.stop = 1; else partner_stop = 1; }
           if (os && !terminal) { if (role == 1) s.stop = 1; else partner_stop = 1; }
+          if (QUIET && s.stop != stop_before) lim = -1.0;         // this ship stops moving: its limit is taken anew
           st_done = s.stop && partner_stop;                       // done needs both stop flags
         }
         out_info = ev | (terminal ? SHIPENV_INFO_TERMINAL : 0) | (ts ? SHIPENV_INFO_TEST_STOP : 0) |
@@ -1716,7 +1876,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (combined_done) out_info |= SHIPENV_INFO_DONE;
       if (MODE == MODE_SUBSTEPS) {
         have_obs = true;
-        k_left -= 1;
+        if (!QUIET) k_left -= 1;
         if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
         else if (k_left <= 0) finalize = true;
       } else {
@@ -1725,13 +1885,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
           if (combined_done) { have_obs = true; flags |= SHIPENV_FLAG_DONE; finalize = true; }
           else if (o_flags & 32) {
             // the obstacle ship is inside the radius of acceptance of its next waypoint
-            if (have_iw) stage = 1;
+            if (have_iw) { stage = 1; if (QUIET) lim = -1.0; }
             else { out_info |= SHIPENV_INFO_UNBOUND | SHIPENV_INFO_DONE; flags |= SHIPENV_FLAG_DONE; finalize = true; }
           }
         } else if (stage == 1) {
           have_obs = true;
           if (combined_done) { flags |= SHIPENV_FLAG_DONE; finalize = true; }
-          else if (sampling_count == G.max_sampling_frequency) { travel_dist = 0.0; travel_time = 0.0; stage = 2; }
+          else if (sampling_count == G.max_sampling_frequency) { travel_dist = 0.0; travel_time = 0.0; stage = 2; if (QUIET) lim = -1.0; }
           else finalize = true;
         } else {
           have_obs = true;
@@ -1744,8 +1904,14 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (EARLY_SWITCH && (my_flags & 64) && !finalize && !(has_stop_branch && s.stop)) {
         s.k += 1;
         refresh_segment(rt, n_iw, s);
+        if (QUIET) lim = -1.0;                                 // new segment, new next waypoint
       }
       }   // !plain_step
+      if (QUIET && !finalize && !(MODE == MODE_STEP && stage == 1) &&
+          !((odo < lim) && (odo < coll_lim) && (k_left > 0 || MODE == MODE_SUBSTEPS))) {
+        // ---- a lane without a valid limit takes everything anew from the state after this step
+        take_limit(p_north, p_east);
+      }
     }
     } while (!__any_sync(FULL_MASK, finalize || lstate == LS_FETCH));
 
@@ -1805,6 +1971,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
     }
   }
 
+#ifdef SENV_QUIET_STATS
+  // measurement build: warp iterations of the simulator loop and how many of them were quiet (spare counters 2, 3)
+  if (lane == 0 && dv.buf.counters) {
+    atomicAdd(&dv.buf.counters[2], (unsigned long long)qs_total);
+    atomicAdd(&dv.buf.counters[3], (unsigned long long)qs_quiet);
+  }
+#endif
   // metric counters: one atomic per warp
   {
     const int sub = __reduce_add_sync(FULL_MASK, total_sub);

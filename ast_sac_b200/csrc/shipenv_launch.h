@@ -18,6 +18,9 @@ struct SenvGrid {
   // of its polygon): the segments that can be the nearest one, within the 1000 m clip, to some point of
   // the cell.  edges[2*c] = segments 0..63, edges[2*c+1] = segments 64..127.
   const unsigned long long* edges;
+  // per cell, the safe radius in metres: a ship whose centre is closer than this to ANY point of the cell has no
+  // corner of its L x L square inside a polygon (no grounding); 0 in and next to polygons.
+  const float* safe;
   double e0, n0, inv_cell;
   double nx_f, ny_f;   // nx, ny as doubles (the bounds test of the cell lookup runs at every simulator step)
   int nx, ny;
