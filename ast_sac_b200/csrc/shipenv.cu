@@ -52,6 +52,8 @@ struct shipenv {
   unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch
   unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
   int streaming_k = SHIPENV_STREAMING_K;    // _step() launches of at most this many steps use a static grid
+  int quiet_min_k = 8;                       // _step() launches of fewer steps take no quiet steps; SHIPENV_QUIET_MIN_K
+  int no_quiet = 0;                          // SHIPENV_QUIET=0: the env kernel takes no quiet steps (comparison runs)
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
   // CUDA events around the env kernel itself (k_env), for shipenv_env_kernel_ms: the step() / _step() entry
   // points also launch the prologue kernel and a memset, which a caller's own events would include
@@ -123,7 +125,7 @@ int validate(const ShipEnvParams* p, long long num_envs) {
 }
 
 SenvView view(const shipenv* h) {
-  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav, h->sm_count,
+  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav, h->sm_count, h->no_quiet,
                   h->log_dev, h->log_count_dev, h->log_envs, h->log_capacity};
 }
 
@@ -185,10 +187,13 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
     }
     CUDA_TRY(cudaEventRecord(h->ev_k0, st));
   }
+  SenvView v = view(h);
+  // quiet steps pay for themselves over a run of steps; a launch of a few steps evaluates every test at every step
+  if (mode == 1 && k < h->quiet_min_k) v.no_quiet = 1;
   cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
-                      ? senv_fast::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
+                      ? senv_fast::launch_env(v, model, h->params.env_kind, mode, actions, k, h->queue_dev,
                                               h->sm_count, persistent, 0, st)
-                      : senv_strict::launch_env(view(h), model, h->params.env_kind, mode, actions, k, h->queue_dev,
+                      : senv_strict::launch_env(v, model, h->params.env_kind, mode, actions, k, h->queue_dev,
                                                 h->sm_count, persistent, 0, st);
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
   if (h->time_kernels) {
@@ -495,6 +500,8 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
   *h->done_host = 0;
   if (const char* pm = getenv("SHIPENV_PERSISTENT")) h->persist_mode = atoi(pm);   // 1 (default), 0, -1 auto
   if (const char* sk = getenv("SHIPENV_STREAMING_K")) h->streaming_k = atoi(sk);    // measurement aid
+  if (const char* q = getenv("SHIPENV_QUIET")) h->no_quiet = (atoi(q) == 0) ? 1 : 0;  // comparison aid (tests)
+  if (const char* q = getenv("SHIPENV_QUIET_MIN_K")) h->quiet_min_k = atoi(q);         // measurement aid
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return SHIPENV_OK;

@@ -1302,12 +1302,12 @@ enum LaneState { LS_FETCH = 0, LS_LOAD = 1, LS_RUN = 2, LS_IDLE = 3 };
 #ifndef SENV_MIN_BLOCKS_SBMPC
 #define SENV_MIN_BLOCKS_SBMPC 4   // measured: 3 CTAs/SM (168 registers, fewer spills) speeds the inactive steps up but slows the evaluation
 #endif
-template <int MODEL, int ENVKIND, int MODE, int COLLAV>
+template <int MODEL, int ENVKIND, int MODE, int COLLAV, int QUIET_STEPS = 1>
 #ifdef SENV_MAXNREG
 __global__ void __maxnreg__(SENV_MAXNREG)
 #else
 __global__ void __launch_bounds__(SENV_ENV_BLOCK, COLLAV == SHIPENV_COLLAV_SBMPC ? SENV_MIN_BLOCKS_SBMPC
-                                  : ((SENV_QUIET != 0) && COLLAV == SHIPENV_COLLAV_NONE && ENVKIND == SHIPENV_ENV_COLAV_IW)
+                                  : ((SENV_QUIET != 0) && (QUIET_STEPS != 0) && COLLAV == SHIPENV_COLLAV_NONE && ENVKIND == SHIPENV_ENV_COLAV_IW)
                                         ? SENV_MIN_BLOCKS_QUIET : SENV_MIN_BLOCKS)
 #endif
 k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned long long* __restrict__ queue) {
@@ -1343,7 +1343,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   constexpr bool IS_IW = ENVKIND != SHIPENV_ENV_COLAV_NONIW;
   // Quiet steps (see the simulator loop): instantiations without collision avoidance and without a per-step reward
-  constexpr bool QUIET = (SENV_QUIET != 0) && COLLAV == SHIPENV_COLLAV_NONE && IS_IW && !IS_RL;
+  // (QUIET_STEPS = 0: the instantiation that evaluates every test at every step -- launches of a few steps, where the
+  //  limits would be taken and never used, and SHIPENV_QUIET=0)
+  constexpr bool QUIET = (SENV_QUIET != 0) && (QUIET_STEPS != 0) && COLLAV == SHIPENV_COLLAV_NONE && IS_IW && !IS_RL;
   // (the NonIW env samples intermediate waypoints too when it is driven with step(action), run_colav/env.py:678-800)
   const bool dynamic_route = (IS_IW || G.obs_sampled_route != 0) && role == 1;
   const MapView mp{G.vert_e, G.vert_n, G.poly_start, sb.bbox, sb.next, G.n_poly, dv.grid};
@@ -2071,13 +2073,19 @@ cudaError_t launch_init_prev(const SenvView& v, cudaStream_t st) {
 
 // persistent grid: as many CTAs as are resident at once (queried per instantiation), never more than
 // the environments need
-template <int MODEL, int ENVKIND, int MODE, int COLLAV>
+template <int MODEL, int ENVKIND, int MODE, int COLLAV, int QUIET_STEPS = 1>
 static void launch_env_inst2(const SenvView& v, const double* actions, int k, unsigned long long* queue,
                              int sm_count, int persistent, cudaStream_t st) {
+  // the instantiations with quiet steps have a twin without them (see k_env)
+  constexpr bool kHasQuiet = (SENV_QUIET != 0) && COLLAV == SHIPENV_COLLAV_NONE && ENVKIND == SHIPENV_ENV_COLAV_IW;
+  if (kHasQuiet && QUIET_STEPS != 0 && v.no_quiet) {
+    launch_env_inst2<MODEL, ENVKIND, MODE, COLLAV, kHasQuiet ? 0 : 1>(v, actions, k, queue, sm_count, persistent, st);
+    return;
+  }
   static int per_sm = 0;
   if (per_sm == 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE, COLLAV>, kEnvBlock, 0) != cudaSuccess || n < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_env<MODEL, ENVKIND, MODE, COLLAV, QUIET_STEPS>, kEnvBlock, 0) != cudaSuccess || n < 1)
       n = SENV_MIN_BLOCKS;
     per_sm = n;
   }
@@ -2085,7 +2093,7 @@ static void launch_env_inst2(const SenvView& v, const double* actions, int k, un
   const long long resident = (long long)per_sm * (sm_count > 0 ? sm_count : 148);
   // persistent: resident CTAs only, lane pairs refill from the queue; otherwise one slot per environment
   const int grid = (int)((persistent && resident < need) ? resident : need);
-  k_env<MODEL, ENVKIND, MODE, COLLAV><<<grid, kEnvBlock, 0, st>>>(v, actions, k, queue);
+  k_env<MODEL, ENVKIND, MODE, COLLAV, QUIET_STEPS><<<grid, kEnvBlock, 0, st>>>(v, actions, k, queue);
 }
 
 template <int MODEL, int ENVKIND, int MODE>
@@ -2172,7 +2180,7 @@ cudaError_t launch_rollout(const SenvView& v, int model, int k, cudaStream_t st)
 }
 
 #else
-template __global__ void k_env<0, 1, 0, 0>(DevView, const double*, int, unsigned long long*);
-template __global__ void k_env<1, 2, 0, 0>(DevView, const double*, int, unsigned long long*);
+template __global__ void k_env<0, 1, 0, 0, 1>(DevView, const double*, int, unsigned long long*);
+template __global__ void k_env<1, 2, 0, 0, 1>(DevView, const double*, int, unsigned long long*);
 #endif
 }  // namespace SENV_NS

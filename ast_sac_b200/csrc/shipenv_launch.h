@@ -33,7 +33,8 @@ struct SenvView {
   long long num_envs;
   SenvGrid grid;
   int collav;  // params->collav (selects the kernel instantiation)
-  int sm_count;  // multiprocessors of the device (the env kernel ranks its warps per SM, see k_env)
+  int sm_count;  // multiprocessors of the device
+  int no_quiet;  // 1: the env kernel evaluates every event test at every step (SHIPENV_QUIET=0; see k_env, quiet steps)
   // optional trajectory log (shipenv_set_trajectory_log)
   double* log_f64;
   int32_t* log_count;

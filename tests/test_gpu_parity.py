@@ -873,3 +873,61 @@ def test_substeps_split_invariance_with_sbmpc():
     sb = env_a.env_f64[[L.EF["sb_p_last"], L.EF["sb_chi_last"]]]
     assert bool(((sb[0] != 1.0) | (sb[1] != 0.0)).any()), "SBMPC never chose a manoeuvre: the scenario does not exercise it"
     env_a.close(); env_b.close()
+
+
+@pytest.mark.parametrize("math_mode", MATH_MODES)
+def test_quiet_steps_are_bit_identical_to_full_evaluation(math_mode, monkeypatch):
+    """The env kernel skips the event tests of a simulator step while every lane of the warp is provably far from its
+    thresholds (quiet steps, shipenv_kernels.cuh).  SHIPENV_QUIET=0 makes the same kernels evaluate every test at every
+    step: both must agree bit for bit -- observations, rewards, info words and step counts after every step() call and
+    every state row at the end -- on 50 000 environments (more than the resident lane pairs: refills), start positions
+    jittered by 400 m (ships that start outside the horizon, next to the islands, next to each other), per-env random
+    scoping angles with a quarter of the environments kept on a collision course; then the same for _step(k)
+    launches of several lengths."""
+    B = 50_000
+    args = S.get_env_args(time_step=4)
+    assets, _ = S.build_colav_assets(args, iw=True)
+    init = S.jittered_init_states(assets, B, pos_jitter_m=400.0, seed=5)
+    monkeypatch.setenv("SHIPENV_QUIET", "0")
+    ref, _ = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init, math_mode=math_mode)
+    monkeypatch.delenv("SHIPENV_QUIET")
+    env, _ = S.prepare_colav_env(args, iw=True, num_envs=B, init_states=init, math_mode=math_mode)
+    gen = torch.Generator().manual_seed(11)
+    actions = ((torch.rand((B, 9), generator=gen, dtype=torch.float64) * 2 - 1) * (np.pi / 6))
+    actions[: B // 4] *= 0.1
+    actions = actions.cuda()
+
+    def same(what):
+        for name in ("obs_buf", "reward_buf", "info_buf", "nsub_buf"):
+            a, b = getattr(env, name), getattr(ref, name)
+            assert torch.equal(a, b), (what, name, int((a != b).sum().item()))
+
+    def same_state(what):
+        for name in ("ship_f64", "ship_i32", "env_f64", "env_i32", "iw_f64"):
+            a, b = getattr(env, name), getattr(ref, name)
+            # (NaN-free by construction; equal_nan is not needed and would hide a divergence)
+            assert torch.equal(a, b), (what, name, int((a != b).sum().item()))
+
+    env.reset(); ref.reset()
+    seen_words = set()
+    for j in range(9):
+        env.step(actions[:, j]); ref.step(actions[:, j])
+        _sync()
+        same(f"step() call {j}")
+        seen_words.update(env.info_buf.to(torch.int64).bitwise_and(L.INFO_EVENT_MASK).unique().tolist())
+    same_state("after the episode")
+    assert env.total_substeps() == ref.total_substeps() > 50 * B
+    assert bool(env.done_mask.all())
+    bits = 0
+    for w in seen_words:
+        bits |= int(w)
+    assert bin(bits).count("1") >= 6, hex(bits)   # collisions, groundings, navigation failures, route ends, horizon ...
+    # _step(k): launches of one step, a few steps, and many steps (k_left is the launch's own counter there)
+    env.reset(); ref.reset()
+    for k in (1, 1, 3, 17, 128, 1, 400, 64):
+        env._step(k); ref._step(k)
+        _sync()
+        same(f"_step({k})")
+    same_state("after the _step() launches")
+    assert env.total_substeps() == ref.total_substeps()
+    env.close(); ref.close()
