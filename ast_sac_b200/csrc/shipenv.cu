@@ -49,10 +49,13 @@ struct shipenv {
   bool owns = false;
   bool constructed = false;
   const double* init_dev = nullptr;   // per-ship initial states given to shipenv_construct (caller-owned)
-  unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch
+  unsigned long long* queue_dev = nullptr;   // [0] work-queue counter, [1] environments done after the launch,
+                                             // [2], [3] split step() calls (launch_env): environments of the second
+                                             // launch, its work-queue counter
   unsigned long long* done_host = nullptr;   // pinned copy of queue_dev[1] of the most recent completed launch
   int streaming_k = SHIPENV_STREAMING_K;    // _step() launches of at most this many steps use a static grid
   int quiet_min_k = 8;                       // _step() launches of fewer steps take no quiet steps; SHIPENV_QUIET_MIN_K
+  int split_calls = 1;                       // step(action) as two launches (see launch_env); SHIPENV_SPLIT_CALLS=0: one
   int no_quiet = 0;                          // SHIPENV_QUIET=0: the env kernel takes no quiet steps (comparison runs)
   int persist_mode = 1;                      // 1 persistent grid + lane-pair refill (default), 0 one slot per environment, -1 auto
   // CUDA events around the env kernel itself (k_env), for shipenv_env_kernel_ms: the step() / _step() entry
@@ -125,7 +128,7 @@ int validate(const ShipEnvParams* p, long long num_envs) {
 }
 
 SenvView view(const shipenv* h) {
-  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav, h->sm_count, h->no_quiet,
+  return SenvView{h->params_dev, h->staged_dev, h->buf, h->num_envs, h->grid, h->params.collav, h->sm_count, h->no_quiet, 0,
                   h->log_dev, h->log_count_dev, h->log_envs, h->log_capacity};
 }
 
@@ -163,18 +166,26 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   // once a noticeable share is done, a persistent grid whose lane pairs refill from the work queue
   // wins (finished environments cost one fetch instead of an idle lane pair).  The share comes from the
   // previous launch's count (copied to pinned memory without a sync, so it may lag by a launch).
+  int persistent = h->persist_mode;
+  if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
+  // step(action) as two launches (SenvView::call_filter, below)
+  const bool has_quiet_twin = h->params.env_kind == SHIPENV_ENV_COLAV_IW && h->params.collav == SHIPENV_COLLAV_NONE;
+  const bool split = mode == 0 && has_quiet_twin && !h->no_quiet && h->split_calls && persistent;
   if (mode == 0) {
     // step(action): the per-environment prologue first, at full width (csrc/shipenv_kernels.cuh k_prologue)
     // (it also restarts the work-queue counters of the env kernel)
+    SenvView pv = view(h);
+    if (split) {
+      pv.call_filter = 1;                    // the prologue counts the environments of the second launch in queue[2]
+      CUDA_TRY(cudaMemsetAsync(h->queue_dev + 2, 0, 2 * sizeof(unsigned long long), st));   // + the second launch's work index
+    }
     cudaError_t pe = (h->params.math_mode == SHIPENV_MATH_FAST)
-                         ? senv_fast::launch_prologue(view(h), h->params.env_kind, actions, h->queue_dev, st)
-                         : senv_strict::launch_prologue(view(h), h->params.env_kind, actions, h->queue_dev, st);
+                         ? senv_fast::launch_prologue(pv, h->params.env_kind, actions, h->queue_dev, st)
+                         : senv_strict::launch_prologue(pv, h->params.env_kind, actions, h->queue_dev, st);
     if (pe != cudaSuccess) return fail(SHIPENV_E_CUDA, "prologue kernel launch: %s", cudaGetErrorString(pe));
   } else {
     CUDA_TRY(cudaMemsetAsync(h->queue_dev, 0, 2 * sizeof(unsigned long long), st));
   }
-  int persistent = h->persist_mode;
-  if (persistent < 0) persistent = (double)(*h->done_host) > 0.08 * (double)h->num_envs ? 1 : 0;
   // (A static grid -- one slot per environment -- for launches of a few _step() was measured and is not the default:
   //  one step per launch reaches 0.42 / 0.79 of the HBM peak at 1e5 / 1e6 environments with the persistent grid, 0.39 /
   //  0.68 with the static one.  SHIPENV_STREAMING_K=k selects it for launches of at most k steps.)
@@ -190,11 +201,26 @@ int launch_env(shipenv* h, int mode, const double* actions, int k, cudaStream_t 
   SenvView v = view(h);
   // quiet steps pay for themselves over a run of steps; a launch of a few steps evaluates every test at every step
   if (mode == 1 && k < h->quiet_min_k) v.no_quiet = 1;
-  cudaError_t e = (h->params.math_mode == SHIPENV_MATH_FAST)
-                      ? senv_fast::launch_env(v, model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                              h->sm_count, persistent, 0, st)
-                      : senv_strict::launch_env(v, model, h->params.env_kind, mode, actions, k, h->queue_dev,
-                                                h->sm_count, persistent, 0, st);
+  auto launch = [&](const SenvView& w) {
+    return (h->params.math_mode == SHIPENV_MATH_FAST)
+               ? senv_fast::launch_env(w, model, h->params.env_kind, mode, actions, k, h->queue_dev, h->sm_count,
+                                       persistent, 0, st)
+               : senv_strict::launch_env(w, model, h->params.env_kind, mode, actions, k, h->queue_dev, h->sm_count,
+                                         persistent, 0, st);
+  };
+  cudaError_t e = cudaSuccess;
+  if (split) {
+    // step(action) as two launches (SenvView::call_filter): environments in the last call of their episode go to the
+    // kernel with quiet steps, the others to its twin; each launch has its own work-queue index, the count of
+    // finished environments is shared
+    SenvView a = v, b = v;
+    a.no_quiet = 1; a.call_filter = 1;
+    b.call_filter = 2;
+    e = launch(a);
+    if (e == cudaSuccess) e = launch(b);
+  } else {
+    e = launch(v);
+  }
   if (e != cudaSuccess) return fail(SHIPENV_E_CUDA, "env kernel launch: %s", cudaGetErrorString(e));
   if (h->time_kernels) {
     CUDA_TRY(cudaEventRecord(h->ev_k1, st));
@@ -482,7 +508,7 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
   }
   rc = build_grid(h);
   if (rc == SHIPENV_OK) rc = build_staged(h);
-  if (rc == SHIPENV_OK && (cudaMalloc(&h->queue_dev, 2 * sizeof(unsigned long long)) != cudaSuccess ||
+  if (rc == SHIPENV_OK && (cudaMalloc(&h->queue_dev, 4 * sizeof(unsigned long long)) != cudaSuccess ||
                            cudaMallocHost(&h->done_host, sizeof(unsigned long long)) != cudaSuccess))
     rc = fail(SHIPENV_E_CUDA, "allocating the work-queue counters failed");
   if (rc) {
@@ -502,6 +528,7 @@ int shipenv_create(const ShipEnvParams* params, int64_t num_envs, int device, sh
   if (const char* sk = getenv("SHIPENV_STREAMING_K")) h->streaming_k = atoi(sk);    // measurement aid
   if (const char* q = getenv("SHIPENV_QUIET")) h->no_quiet = (atoi(q) == 0) ? 1 : 0;  // comparison aid (tests)
   if (const char* q = getenv("SHIPENV_QUIET_MIN_K")) h->quiet_min_k = atoi(q);         // measurement aid
+  if (const char* q = getenv("SHIPENV_SPLIT_CALLS")) h->split_calls = atoi(q);         // measurement aid
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
   *out = h;
   return SHIPENV_OK;

@@ -1207,14 +1207,22 @@ k_prologue(DevView dv, const double* __restrict__ actions, unsigned long long* _
   const ShipEnvParams& G = *dv.params;
   const long long B = dv.num_envs;
   const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (env >= B) return;
   constexpr bool IS_RL = ENVKIND == SHIPENV_ENV_RL;
   int* ei = dv.buf.env_i32;
   double* ef = dv.buf.env_f64;
-  int flags = ei[SHIPENV_EI_FLAGS * B + env];
+  int flags = (env < B) ? ei[SHIPENV_EI_FLAGS * B + env] : SHIPENV_FLAG_DONE;
+  int sampling_count = (env < B) ? ei[SHIPENV_EI_SAMPLING_COUNT * B + env] : -1;
+  if (dv.call_filter != 0) {
+    // queue[2] (zeroed by the host): environments the second launch of this call will take (SenvView::call_filter) --
+    // those whose sampling count, after this prologue, is the maximum; either launch returns at once when it has none
+    const bool live = (env < B) && !(flags & SHIPENV_FLAG_DONE);
+    const int after = sampling_count + ((live && sampling_count < G.max_sampling_frequency) ? 1 : 0);
+    const unsigned last = __ballot_sync(FULL_MASK, env < B && after == G.max_sampling_frequency);
+    if ((threadIdx.x & 31) == 0 && last) atomicAdd(&queue[2], (unsigned long long)__popc(last));
+  }
+  if (env >= B) return;
   if (flags & SHIPENV_FLAG_DONE) return;                      // k_env reports it as already done
   flags &= ~SHIPENV_FLAG_HAVE_IW;
-  int sampling_count = ei[SHIPENV_EI_SAMPLING_COUNT * B + env];
   if (sampling_count < G.max_sampling_frequency) {
     const MapView mp{G.vert_e, G.vert_n, G.poly_start, nullptr, nullptr, G.n_poly, dv.grid};
     const double a = actions[env];
@@ -1319,6 +1327,13 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
   // decided right after the integration of step t and carried out in the event path below; SBMPC's extra
   // los_guidance call runs on the segment BEFORE the switch (quirk 2), so those instantiations keep it at the top.
   constexpr bool EARLY_SWITCH = !SBMPC;
+  if (MODE == MODE_STEP && dv.call_filter != 0) {
+    // one of the two launches of a step(action) call (SenvView::call_filter): nothing to do when the other has it all
+    const unsigned long long n_last = queue[2];
+    if (dv.call_filter == 2 ? (n_last == 0ull) : (n_last == (unsigned long long)dv.num_envs)) return;
+  }
+  // work-queue index: queue[0]; the second launch of a split call draws from queue[3] (both zeroed before the first)
+  unsigned long long* const work_q = queue + ((MODE == MODE_STEP && dv.call_filter == 2) ? 3 : 0);
   __shared__ SharedBlock sb_static;
   stage_params(sb_static, dv.staged);
   const int lane = (int)(threadIdx.x & 31);
@@ -1457,7 +1472,7 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       if (want) {
         const int leader = __ffs(want) - 1;
         unsigned long long base = 0;
-        if (lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(want));
+        if (lane == leader) base = atomicAdd(work_q, (unsigned long long)__popc(want));
         base = __shfl_sync(FULL_MASK, base, leader);
         long long mine = n_slots + (long long)base + __popc(want & ((1u << lane) - 1u));
         mine = __shfl_sync(FULL_MASK, mine, lane & ~1);       // the obstacle lane takes its partner's index
@@ -1472,6 +1487,11 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
 
     // ---------------- (2) load the environment and run the step(action) prologue
     bool finalize = false;                // store this environment at the end of the iteration
+    if (MODE == MODE_STEP && dv.call_filter != 0 && lstate == LS_LOAD) {
+      // this launch takes only one kind of environment (SenvView::call_filter); the other launch of the call has the rest
+      const bool last_call = dv.buf.env_i32[env] == G.max_sampling_frequency;     // row SHIPENV_EI_SAMPLING_COUNT
+      if ((dv.call_filter == 2) != last_call) lstate = LS_FETCH;
+    }
     if (lstate == LS_LOAD) {
       const long long sidx = 2 * env + role;
       load_ship(dv, n_ships, sidx, s);

@@ -34,7 +34,12 @@ struct SenvView {
   SenvGrid grid;
   int collav;  // params->collav (selects the kernel instantiation)
   int sm_count;  // multiprocessors of the device
-  int no_quiet;  // 1: the env kernel evaluates every event test at every step (SHIPENV_QUIET=0; see k_env, quiet steps)
+  int no_quiet;  // 1: launch the env kernel's twin that evaluates every event test at every step (see k_env, quiet steps)
+  // step(action) launches only -- 0: every environment; 1: only environments NOT in the last step() call of their
+  // episode (sampling count below the maximum); 2: only those that are.  The last call runs the environment to its end
+  // (hundreds of steps: quiet steps pay), the others end after ~85 steps at the next waypoint (they do not), so the host
+  // issues the call as two launches, one per twin; an environment is taken by exactly one of them.
+  int call_filter;
   // optional trajectory log (shipenv_set_trajectory_log)
   double* log_f64;
   int32_t* log_count;

@@ -59,6 +59,12 @@ def device_source_hash() -> str:
     return h.hexdigest()[:16]
 
 
+def split_calls(a) -> bool:
+    """Does the library issue this workload's step() calls as two k_env launches (csrc/shipenv.cu launch_env)."""
+    return (a.workload == "colav_iw" and a.collav == "none" and os.environ.get("SHIPENV_SPLIT_CALLS", "1") != "0"
+            and os.environ.get("SHIPENV_QUIET", "1") != "0" and os.environ.get("SHIPENV_PERSISTENT", "1") != "0")
+
+
 def kernel_counts(workload: str, collav: str):
     """(entry or None, stale flag) of profiles/kernel_counts.json for this workload."""
     try:
@@ -562,7 +568,9 @@ def run_b200(a, rank, local_rank, world):
             "env_steps_per_episode_mean": m["steps_done"] / n_episodes / B,
             "wall_s_timed_region": float(allagg[:, 2].max()), "device_s_timed_region": max_time,
             "clocks": clocks, "cpu_pinning": pin,
-            "gpu_launches": int(n_episodes * (1 + 2 * N_RL_STEPS)),     # k_reset + 9 x (k_prologue + k_env) per episode
+            # k_reset + 9 x (k_prologue + k_env) per episode; the colav_iw env without collision avoidance issues every
+            # step() call as two k_env launches (quiet-step twin for environments in their last call)
+            "gpu_launches": int(n_episodes * (1 + (3 if split_calls(a) else 2) * N_RL_STEPS)),
             "launch_ms_mean": [round(float(x), 4) for x in launch_ms.mean(axis=0)],
             "launch_env_steps": launch_steps,
             "roofline": roofline, "roofline_hbm_k1": roofline_k1,

@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--skip", type=int, required=True, help="the -s value of the ncu capture (k_env launches skipped)")
     ap.add_argument("--envs", type=int, required=True)
     ap.add_argument("--source", default=None, help="name of the committed ncu summary the numbers come from")
+    ap.add_argument("--split", action="store_true",
+                    help="every step() call is two k_env launches (SenvView::call_filter): captured launches 2j, 2j + 1 "
+                         "belong to call (skip / 2 + j) mod 9 and are added up")
     a = ap.parse_args()
     csv.field_size_limit(10 ** 9)
     rows = list(csv.reader(open(a.raw)))
@@ -46,7 +49,7 @@ def main():
         raise SystemExit("run bench.py with --workload/--collav of the key so that launch_env_steps belongs to it")
     out = []
     for i, r in enumerate(data):
-        n = steps_per_launch[(a.skip + i) % 9]
+        n = steps_per_launch[((a.skip + i) // 2) % 9] if a.split else steps_per_launch[(a.skip + i) % 9]
         cyc = col(hdr, r, "sm__cycles_elapsed.max")
 
         def total(op):
@@ -70,7 +73,28 @@ def main():
                     "achieved_occupancy_pct": col(hdr, r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                     "threads_per_inst": col(hdr, r, "smsp__thread_inst_executed_per_inst_executed.ratio"),
                     "duration_us": col(hdr, r, "gpu__time_duration.sum")})
-    mean = lambda k: sum(o[k] for o in out) / len(out)
+    if a.split:
+        # add the two launches of a call up; percentages weighted by duration
+        calls = []
+        for j in range(0, len(out) - 1, 2):
+            p, q = out[j], out[j + 1]
+            n, t = p["env_steps"], p["duration_us"] + q["duration_us"]
+            w = lambda k: (p[k] * p["duration_us"] + q[k] * q["duration_us"]) / t
+            calls.append({"env_steps": n,
+                          "fp64_inst_per_env_step": p["fp64_inst_per_env_step"] + q["fp64_inst_per_env_step"],
+                          "flop_exec_per_env_step": p["flop_exec_per_env_step"] + q["flop_exec_per_env_step"],
+                          "dram_bytes": p["dram_bytes"] + q["dram_bytes"], "pipe_fp64_pct": w("pipe_fp64_pct"),
+                          "issue_active_pct": w("issue_active_pct"), "achieved_occupancy_pct": w("achieved_occupancy_pct"),
+                          "threads_per_inst": w("threads_per_inst"), "duration_us": t,
+                          "duration_us_launches": [p["duration_us"], q["duration_us"]]})
+        out = calls
+        # per env-step figures of the whole capture: weighted by the simulator steps of each call
+        tot = sum(o["env_steps"] for o in out)
+        mean = lambda k: (sum(o[k] * o["env_steps"] for o in out) / tot if k.endswith("per_env_step")
+                          else (sum(o[k] * o["duration_us"] for o in out) / sum(o["duration_us"] for o in out)
+                                if k.endswith("_pct") or k == "threads_per_inst" else sum(o[k] for o in out) / len(out)))
+    else:
+        mean = lambda k: sum(o[k] for o in out) / len(out)
     try:
         d = json.load(open(bench.KERNEL_COUNTS))
     except Exception:
