@@ -441,6 +441,15 @@ def roofline_block(workload, collav, B, m, n_episodes, fp64_peak):
         "fp64_pipe_active_pct_ncu": None if (counts is None or stale) else counts.get("pipe_fp64_pct"),
         "issue_slots_active_pct_ncu": None if (counts is None or stale) else counts.get("issue_active_pct"),
         "counts_source": None if counts is None else counts.get("source"),
+        # What the executed count covers.  A capture of every launch of an episode counts what the ships really execute:
+        # in the last step() call a third of the ship-steps belong to ships that have stopped (they only advance their
+        # clock), so the episode's count per env-step is below the count of a call in which both ships sail -- and below
+        # SURVEY section 8(d)'s algorithmic figure, which assumes two sailing ships.  Rounds 1 / 2 (first sessions) quoted
+        # the fraction with the mid-episode count applied to every env-step: `frac_midcall_count` is that figure.
+        "flop_count_scope": None if counts is None else counts.get("scope", "two mid-episode step() calls"),
+        "flop_per_env_step_executed_midcall": None if counts is None else counts.get("flop_exec_per_env_step_midcall"),
+        "frac_midcall_count": None if (counts is None or stale or not counts.get("flop_exec_per_env_step_midcall")) else
+                              counts["flop_exec_per_env_step_midcall"] * env_steps / kernel_s / 1e12 / fp64_peak,
         "traffic": None if (counts is None or stale or B != counts.get("envs")) else counts.get("dram_bytes_per_launch"),
         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/)",
         "algorithmic_bytes_per_launch": float(B * (2 * (17 * 8 + 4) * 2 + 2 * (5 * 8 + 8) + 48)),
