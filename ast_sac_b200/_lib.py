@@ -79,7 +79,7 @@ EXPORTS = [
     "shipenv_construct", "shipenv_reset", "shipenv_init_step", "shipenv_step", "shipenv_substeps",
     "shipenv_ship_rollout", "shipenv_reset_host", "shipenv_step_host", "shipenv_substeps_host",
     "shipenv_read_counters", "shipenv_measure_fp64_peak", "shipenv_selftest_math", "shipenv_set_trajectory_log",
-    "shipenv_time_env_kernel", "shipenv_env_kernel_ms", "shipenv_map_query",
+    "shipenv_time_env_kernel", "shipenv_env_kernel_ms", "shipenv_map_query", "shipenv_map_safe_radius",
     "shipenv_register_host", "shipenv_unregister_host",
 ]
 
@@ -123,6 +123,7 @@ def load():
     L.shipenv_register_host.argtypes = [vp, vp, C.c_size_t]
     L.shipenv_unregister_host.argtypes = [vp, vp]
     L.shipenv_map_query.argtypes = [vp, i64, vp, vp, C.c_double, vp, vp, vp, vp]
+    L.shipenv_map_safe_radius.argtypes = [vp, i64, vp, vp, vp, vp]
     if L.shipenv_abi_version() != ABI_VERSION:
         raise ImportError("libshipenv.so ABI version mismatch; rebuild the extension")
     if L.shipenv_sizeof_params() != C.sizeof(Params):

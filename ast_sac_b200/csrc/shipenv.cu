@@ -872,6 +872,18 @@ int shipenv_map_query(shipenv_t* h, int64_t n, const double* north_dev, const do
   return SHIPENV_OK;
 }
 
+int shipenv_map_safe_radius(shipenv_t* h, int64_t n, const double* north_dev, const double* east_dev, float* out_dev,
+                            void* stream) {
+  if (!h) return fail(SHIPENV_E_ARG, "handle is NULL");
+  if (n <= 0 || !north_dev || !east_dev || !out_dev) return fail(SHIPENV_E_ARG, "bad arguments");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY((h->params.math_mode == SHIPENV_MATH_FAST)
+               ? senv_fast::launch_map_safe_radius(view(h), n, north_dev, east_dev, out_dev, st)
+               : senv_strict::launch_map_safe_radius(view(h), n, north_dev, east_dev, out_dev, st));
+  return SHIPENV_OK;
+}
+
 int shipenv_selftest_math(int device, int64_t n, uint64_t seed, unsigned long long* mismatches_host) {
   if (!mismatches_host || n <= 0) return fail(SHIPENV_E_ARG, "bad arguments");
   int count = 0;

@@ -9,6 +9,10 @@
 // per-env state is structure-of-arrays in HBM (include/shipenv.h) so every load/store of a warp is
 // one contiguous 256-byte (FP64) or 128-byte (int32) segment.
 //
+// The run_colav IW env without collision avoidance additionally skips the per-step event tests while every lane of
+// the warp is provably far from all of its thresholds ("quiet steps", k_env): same results bit for bit, checked
+// against the twin instantiation that evaluates everything at every step.
+//
 // Arithmetic is IEEE FP64 with the reference's forward-Euler scheme and operation order; the file is
 // compiled with -fmad=false so a*b+c is two roundings, as in CPython/NumPy.
 // Citations are paths relative to the reference root.
@@ -1730,8 +1734,9 @@ k_env(DevView dv, const double* __restrict__ actions, int k_substeps, unsigned l
       }
     }
     // ---- the ships meet: positions both ways, then one word of partial flags per ship.  Almost every
-    // simulator step is "quiet" (no termination / stop condition holds for either ship, no collision, no
-    // radius of acceptance reached): those steps skip the event bookkeeping below altogether.
+    // simulator step is "plain" (no termination / stop condition holds for either ship, no collision, no
+    // radius of acceptance reached): those steps skip the event bookkeeping below altogether.  (The instantiations
+    // with quiet steps, above, come here only when some lane of the warp cannot rule its tests out.)
     const double p_north = shfl_xor_f64(s.north, 1);
     const double p_east = shfl_xor_f64(s.east, 1);
     // bits of my_flags: 1 grounding, 2 navigation failure, 4 reached the route end, 8 outside the map horizon,
@@ -2066,6 +2071,16 @@ k_map_query(DevView dv, long long n, const double* __restrict__ north, const dou
   distance[i] = map_distance(mp, pn, pe);
 }
 
+// the quiet steps' safe radius (map_safe_radius) at caller-given points: test probe
+__global__ void __launch_bounds__(128)
+k_map_safe_radius(DevView dv, long long n, const double* __restrict__ north, const double* __restrict__ east,
+                  float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const MapView mp{nullptr, nullptr, nullptr, nullptr, nullptr, 0, dv.grid};
+  out[i] = map_safe_radius(mp, (float)north[i], (float)east[i]);
+}
+
 #ifndef SENV_ONLY_ONE
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (declared in shipenv_launch.h)
@@ -2189,6 +2204,12 @@ cudaError_t launch_map_query(const SenvView& v, long long n, const double* north
                              double ship_length, int* contains, int* square, double* distance, cudaStream_t st) {
   k_map_query<<<(int)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(v, n, north, east, ship_length, contains, square,
                                                                    distance);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_map_safe_radius(const SenvView& v, long long n, const double* north, const double* east, float* out,
+                                   cudaStream_t st) {
+  k_map_safe_radius<<<(int)((n + kBlock - 1) / kBlock), kBlock, 0, st>>>(v, n, north, east, out);
   return cudaGetLastError();
 }
 

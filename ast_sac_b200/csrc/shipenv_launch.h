@@ -62,6 +62,8 @@ struct SenvView {
   cudaError_t launch_map_query(const SenvView& v, long long n, const double* north, const double* east,        \
                                double ship_length, int* contains, int* square, double* distance,               \
                                cudaStream_t st);                                                               \
+  cudaError_t launch_map_safe_radius(const SenvView& v, long long n, const double* north, const double* east,  \
+                                     float* out, cudaStream_t st);                                             \
   cudaError_t launch_math_selftest(long long n, unsigned long long seed, unsigned long long* mismatches_dev,   \
                                    cudaStream_t st);                                                           \
   }

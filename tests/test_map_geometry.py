@@ -117,3 +117,57 @@ def test_cuda_geometry_against_exact_arithmetic(math_mode):
                    for dn in (-half, half) for de in (-half, half))
         assert bool(square[i]) == bool(want), (i, g["north"][i], g["east"][i])
     env.close()
+
+
+@pytest.mark.gpu
+def test_safe_radius_bounds_the_four_corner_test():
+    """The quiet steps of the env kernel skip the grounding test of a ship that has moved less than the safe radius
+    it read at some earlier position.  The invariant behind that, checked against the kernel's own
+    four-corner test: around every point with a positive radius, no position within the radius is grounded -- 64
+    positions per point, half of them right at the rim -- and the radius is not vacuous (open water reads hundreds of
+    metres, points inside an island read 0)."""
+    import torch
+    from ast_sac_b200 import _lib as L
+    from ast_sac_b200 import scenarios as S
+    args = S.get_env_args(time_step=4)
+    env, assets = S.prepare_colav_env(args, iw=True, num_envs=1)
+    lib = L.load()
+    ship_length = max(a.ship_model.l_ship for a in assets)
+    gen = torch.Generator().manual_seed(3)
+    n = 200_000
+    north = (torch.rand(n, generator=gen, dtype=torch.float64) * 10400.0 - 200.0).cuda()     # a margin outside the map too
+    east = (torch.rand(n, generator=gen, dtype=torch.float64) * 20400.0 - 200.0).cuda()
+    radius = torch.zeros(n, dtype=torch.float32, device="cuda")
+    L.check(lib.shipenv_map_safe_radius(env._handle, n, north.data_ptr(), east.data_ptr(), radius.data_ptr(),
+                                        env._stream_ptr()))
+    torch.cuda.synchronize()
+    outside = (north < 0) | (north >= 10000.0) | (east < 0) | (east >= 20000.0)
+    assert bool((radius[outside] == 0).all())
+    pos = radius > 0
+    assert 0.25 < float(pos.double().mean()) < 0.75           # the islands cover ~40 % of the map
+    assert float(radius.max()) > 1500.0
+    pn, pe, r = north[pos], east[pos], radius[pos].double()
+    m = int(pos.sum())
+    dummy_i = torch.zeros(m, dtype=torch.int32, device="cuda")
+    dummy_d = torch.zeros(m, dtype=torch.float64, device="cuda")
+    square = torch.zeros(m, dtype=torch.int32, device="cuda")
+    grounded = 0
+    for j in range(64):
+        ang = torch.rand(m, generator=gen, dtype=torch.float64).cuda() * (2 * np.pi)
+        frac = torch.ones(m, dtype=torch.float64, device="cuda") if j % 2 else torch.rand(m, generator=gen, dtype=torch.float64).cuda()
+        qn = pn + r * frac * torch.cos(ang)
+        qe = pe + r * frac * torch.sin(ang)
+        L.check(lib.shipenv_map_query(env._handle, m, qn.data_ptr(), qe.data_ptr(), float(ship_length),
+                                      dummy_i.data_ptr(), square.data_ptr(), dummy_d.data_ptr(), env._stream_ptr()))
+        torch.cuda.synchronize()
+        grounded += int(square.sum())
+    assert grounded == 0
+    # a point inside an island reads 0 (MAP_DATA polygon 0 contains (east 2000, north 8000))
+    one_n = torch.tensor([8000.0], dtype=torch.float64, device="cuda")
+    one_e = torch.tensor([2000.0], dtype=torch.float64, device="cuda")
+    one_r = torch.ones(1, dtype=torch.float32, device="cuda")
+    L.check(lib.shipenv_map_safe_radius(env._handle, 1, one_n.data_ptr(), one_e.data_ptr(), one_r.data_ptr(),
+                                        env._stream_ptr()))
+    torch.cuda.synchronize()
+    assert float(one_r[0]) == 0.0
+    env.close()
