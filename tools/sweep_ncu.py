@@ -22,7 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METRICS = ["gpu__time_duration.sum", "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum",
            "smsp__sass_thread_inst_executed_op_dadd_pred_on.sum", "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum",
            "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
-           "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]
+           "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+           "smsp__issue_active.avg.pct_of_peak_sustained_active"]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0,
         "usecond": 1e-6, "nsecond": 1e-9, "msecond": 1e-3, "second": 1.0}
 
@@ -32,7 +33,10 @@ def capture(workload, envs, regime, k):
         log = os.path.join(td, "ncu.csv")
         cmd = ["ncu", "--metrics", ",".join(METRICS), "--clock-control", "none", "-k", "regex:k_env", "--csv", "--log-file", log]
         if regime == "episode":
-            cmd += ["-s", "9", "-c", "9"]          # skip the warm-up episode's 9 launches, take the measured episode
+            # skip the warm-up episode's launches, take the measured episode (the colav_iw env issues every step() call as
+            # two k_env launches)
+            n = 18 if (workload == "colav_iw" and os.environ.get("SHIPENV_SPLIT_CALLS", "1") != "0") else 9
+            cmd += ["-s", str(n), "-c", str(n)]
         sweep = [sys.executable, os.path.join(ROOT, "tools", "scaling_sweep.py"), "--workload", workload, "--envs", str(envs),
                  "--repeats", "1", "--regimes", "episode" if regime == "episode" else "substeps", "--ks", str(k or 1),
                  "--substeps-total", str(max(k or 1, 32))]
@@ -52,10 +56,11 @@ def capture(workload, envs, regime, k):
     dram = sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in launches)
     occ = sum(l[METRICS[6]] * l["gpu__time_duration.sum"] for l in launches) / t
     pipe = sum(l[METRICS[7]] * l["gpu__time_duration.sum"] for l in launches) / t
+    issue = sum(l[METRICS[8]] * l["gpu__time_duration.sum"] for l in launches) / t
     line = [json.loads(x) for x in out.stdout.strip().split("\n") if x.startswith("{")]
     return {"envs_total": envs, "n_gpus": 1, "workload": workload, "regime": "episode" if regime == "episode" else f"substeps k={k}",
             "ncu_launches": len(launches), "ncu_kernel_s": t, "ncu_fp64_tflops": flop / t / 1e12, "ncu_dram_gbs": dram / t / 1e9,
-            "ncu_achieved_occupancy_pct": occ, "ncu_pipe_fp64_active_pct": pipe,
+            "ncu_achieved_occupancy_pct": occ, "ncu_pipe_fp64_active_pct": pipe, "ncu_issue_active_pct": issue,
             "env_steps_under_ncu": line[-1]["env_steps"] if line else None}
 
 
